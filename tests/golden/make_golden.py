@@ -1,0 +1,181 @@
+"""Generate golden vectors by running the UNMODIFIED reference from /root/reference on CPU.
+
+Run once in the build container (the reference cannot travel to the GPU box):
+    python tests/golden/make_golden.py
+Writes tests/golden/{ops_golden,generator_g32,generator_g128,audio_glue}.npz.  Inputs are derived from
+numpy PCG64 seeds (oracle.stylegan2_oracle.synth_state_dict), so the fixtures only store the reference's OUTPUTS
+(images + strided samples of the activation maps) and small inputs.
+
+The reference's JIT build of its CUDA ops is stubbed out (`torch.utils.cpp_extension.load`): on CPU the
+reference dispatches to its own Python fallbacks (`op/upfirdn2d.py:146-149`, `op/fused_act.py:87-94`), which
+is exactly the oracle the survey names.  librosa/madmom/kornia/matplotlib are absent and
+are stubbed so that `import audioreactive` succeeds; only the pure torch/scipy functions are exercised.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+
+def import_reference():
+    import torch.utils.cpp_extension as cpp
+
+    cpp.load = lambda *a, **k: types.SimpleNamespace()  # CPU path never touches the extension
+    for name in ["librosa", "librosa.display", "madmom", "matplotlib", "matplotlib.pyplot", "matplotlib.patches",
+                 "kornia", "kornia.augmentation", "kornia.geometry", "kornia.geometry.transform", "ffmpeg"]:
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            sys.modules[name] = m
+    sys.path.insert(0, REF)
+    import op  # noqa
+    from models import stylegan2 as ref_sg2
+    import audioreactive as ar
+    return op, ref_sg2, ar
+
+
+def strided(t, n=6):
+    """Deterministic sub-sample of an activation map: every k-th channel, all pixels up to 32x32 then strided."""
+    c = t.shape[1]
+    cs = max(c // n, 1)
+    s = max(t.shape[2] // 32, 1)
+    return t[:, ::cs, ::s, ::s].contiguous().numpy()
+
+
+def gen_case(ref_sg2, size, cm, batch, seed, psi_lo):
+    from oracle import stylegan2_oracle as O
+
+    sd = O.synth_state_dict(size, channel_multiplier=cm, seed=seed)
+    g = ref_sg2.Generator(size, 512, 8, channel_multiplier=cm, constant_input=True, output_size=size)
+    missing, unexpected = g.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(".kernel" in m or "noises" in m for m in missing), missing
+    g.eval()
+    rng = np.random.Generator(np.random.PCG64(seed + 1000))
+    log_size, num_layers, n_latent = O.layout(size)
+    z = torch.from_numpy(rng.standard_normal((batch, 512)).astype(np.float32))
+    with torch.no_grad():
+        w = g.get_latent(z)  # 2-D path of the mapping network (CPU == CUDA)
+        latent = w[:, None, :].repeat(1, n_latent, 1)
+        latent = latent + 0.05 * torch.from_numpy(rng.standard_normal(latent.shape).astype(np.float32))  # W+
+        noise = [torch.from_numpy(rng.standard_normal((batch, 1, 2 ** ((l + 5) // 2), 2 ** ((l + 5) // 2))).astype(np.float32))
+                 for l in range(num_layers)]
+        noise[2] = None  # exercise the buffer path (randomize_noise=False)
+        psi = torch.from_numpy(rng.uniform(psi_lo, 1.0, batch).astype(np.float32))
+        tl = w.mean(0, keepdim=True) * 0.5
+        g.truncation_latent = tl
+        image, acts = g(latent, noise=list(noise), truncation=psi, input_is_latent=True, randomize_noise=False,
+                        return_activation_maps=True)
+    out = {"size": size, "cm": cm, "seed": seed, "z": z.numpy(), "w": w.numpy(), "latent": latent.numpy(),
+           "psi": psi.numpy(), "truncation_latent": tl.numpy(), "image": image.numpy(), "noise_none": np.array([2])}
+    for l, n in enumerate(noise):
+        if n is not None:
+            out[f"noise_{l}"] = n.numpy()
+    for l, a in enumerate(acts):
+        out[f"act_{l}"] = strided(a)
+        out[f"act_{l}_absmax"] = np.array(a.abs().max().item(), np.float32)
+    return out
+
+
+def ops_cases(op):
+    rng = np.random.Generator(np.random.PCG64(7))
+    out = {}
+    k4 = (np.outer([1, 3, 3, 1], [1, 3, 3, 1]) / 64.0).astype(np.float32)
+    sym6 = np.array([0.015404109327027373, 0.0034907120842174702, -0.11799011114819057, -0.048311742585633,
+                     0.4910559419267466, 0.787641141030194, 0.3379294217276218, -0.07263752278646252,
+                     -0.021060292512300564, 0.04472490177066578, 0.0017677118642428036, -0.007800708325034148],
+                    dtype=np.float64)
+    k12 = np.outer(sym6, sym6).astype(np.float32)
+    k3 = rng.standard_normal((3, 3)).astype(np.float32)
+    k2 = rng.standard_normal((2, 2)).astype(np.float32)
+    k43 = rng.standard_normal((4, 3)).astype(np.float32)
+    cases = [
+        ("blur9", (2, 3, 9, 9), k4 * 4, 1, 1, (1, 1)),
+        ("blur9x17", (2, 3, 9, 17), k4 * 4, 1, 1, (1, 1)),
+        ("blur65", (1, 5, 65, 65), k4 * 4, 1, 1, (1, 1)),
+        ("blur129x33", (1, 2, 129, 33), k4 * 4, 1, 1, (1, 1)),
+        ("up8", (2, 3, 8, 8), k4 * 4, 2, 1, (2, 1)),
+        ("up4x8", (2, 3, 4, 8), k4 * 4, 2, 1, (2, 1)),
+        ("up37", (1, 3, 37, 21), k4 * 4, 2, 1, (2, 1)),
+        ("down16", (2, 4, 16, 16), k4, 1, 2, (1, 1)),
+        ("down17pad2", (1, 2, 17, 23), k4, 1, 2, (2, 2)),
+        ("k3same", (1, 3, 12, 10), k3, 1, 1, (1, 1)),
+        ("k2up2", (1, 3, 7, 9), k2, 2, 1, (1, 0)),
+        ("k43asym", (1, 2, 11, 13), k43, 1, 1, (2, 1)),
+        ("negpad", (1, 2, 16, 16), k4, 1, 1, (-1, -2)),
+        ("negpad_up", (1, 2, 10, 12), k4 * 4, 2, 1, (-1, 3)),
+        ("sym6_up2", (1, 2, 20, 20), k12 * 4, 2, 1, (6, 5)),
+        ("sym6_down2", (1, 2, 40, 40), k12, 1, 2, (5, 5)),
+        ("up3down2", (1, 2, 9, 9), k4, 3, 2, (2, 2)),
+        ("tiny1", (1, 1, 1, 1), k4 * 4, 2, 1, (2, 1)),
+    ]
+    names = []
+    for name, shape, k, up, down, pad in cases:
+        x = rng.standard_normal(shape).astype(np.float32)
+        y = op.upfirdn2d(torch.from_numpy(x), torch.from_numpy(k), up=up, down=down, pad=pad).numpy()
+        out[f"ufd_{name}_x"] = x
+        out[f"ufd_{name}_k"] = k
+        out[f"ufd_{name}_cfg"] = np.array([up, down, pad[0], pad[1]])
+        out[f"ufd_{name}_y"] = y
+        names.append(name)
+    out["ufd_names"] = np.array(names)
+    # fused_leaky_relu CPU fallback: 2-D and 4-D (`op/fused_act.py:87-94`)
+    for name, shape in (("fl2d", (5, 512)), ("fl4d", (2, 6, 5, 7)), ("fl4d_big", (1, 32, 16, 16))):
+        x = rng.standard_normal(shape).astype(np.float32)
+        b = rng.standard_normal(shape[1]).astype(np.float32)
+        y = op.fused_leaky_relu(torch.from_numpy(x), torch.from_numpy(b)).numpy()
+        out[f"{name}_x"], out[f"{name}_b"], out[f"{name}_y"] = x, b, y
+    return out
+
+
+def audio_glue_cases(ar):
+    """Pure torch/scipy functions of audioreactive/ that run without librosa."""
+    rng = np.random.Generator(np.random.PCG64(11))
+    out = {}
+    ar.set_SMF(1)
+    x1 = torch.from_numpy(rng.standard_normal(200).astype(np.float32))
+    x3 = torch.from_numpy(rng.standard_normal((120, 6, 16)).astype(np.float32))
+    x4 = torch.from_numpy(rng.standard_normal((64, 1, 4, 8)).astype(np.float32))
+    out["gf_x1"], out["gf_x3"], out["gf_x4"] = x1.numpy(), x3.numpy(), x4.numpy()
+    out["gf_y1_s5_c0"] = ar.gaussian_filter(x1.clone(), 5, causal=0).numpy()
+    out["gf_y1_s3"] = ar.gaussian_filter(x1.clone(), 3).numpy()
+    out["gf_y3_s4"] = ar.gaussian_filter(x3.clone(), 4).numpy()
+    out["gf_y3_s2_c02"] = ar.gaussian_filter(x3.clone(), 2, causal=0.2).numpy()
+    out["gf_y4_s5"] = ar.gaussian_filter(x4.clone(), 5).numpy()
+    out["gf_y4_s128"] = ar.gaussian_filter(x4.clone(), 128).numpy()  # radius > n_frames branch (:350-355)
+    env = torch.from_numpy(np.abs(rng.standard_normal(300)).astype(np.float32))
+    env = ar.gaussian_filter(env, 2)
+    out["pc_x"] = env.numpy()
+    out["pc_y97"] = ar.percentile_clip(env.clone(), 97).numpy()
+    out["pc_y50"] = ar.percentile_clip(env.clone(), 50).numpy()
+    chroma = torch.from_numpy(rng.uniform(0, 1, (50, 12)).astype(np.float32))
+    chroma = chroma / chroma.sum(1, keepdim=True)
+    sel = torch.from_numpy(rng.standard_normal((12, 6, 64)).astype(np.float32))
+    out["cw_chroma"], out["cw_sel"] = chroma.numpy(), sel.numpy()
+    out["cw_y"] = ar.chroma_weight_latents(chroma, sel).numpy()
+    n = torch.from_numpy(rng.uniform(-1, 3, 77).astype(np.float32))
+    out["norm_x"] = n.numpy()
+    out["norm_y"] = ar.normalize(n.clone()).numpy()
+    return out
+
+
+def main():
+    op, ref_sg2, ar = import_reference()
+    torch.set_grad_enabled(False)
+    np.savez_compressed(os.path.join(HERE, "ops_golden.npz"), **ops_cases(op))
+    np.savez_compressed(os.path.join(HERE, "generator_g32.npz"), **gen_case(ref_sg2, 32, 2, 2, seed=3, psi_lo=0.5))
+    np.savez_compressed(os.path.join(HERE, "generator_g128.npz"), **gen_case(ref_sg2, 128, 1, 1, seed=5, psi_lo=0.7))
+    np.savez_compressed(os.path.join(HERE, "audio_glue.npz"), **audio_glue_cases(ar))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,73 @@
+"""The oracle is pinned against fixtures produced by the UNMODIFIED reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops_oracle as OO
+from oracle import stylegan2_oracle as O
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def test_upfirdn2d_oracle_matches_reference_native(golden_dir):
+    g = _load(golden_dir, "ops_golden.npz")
+    for name in g["ufd_names"]:
+        x, k, cfg, y = g[f"ufd_{name}_x"], g[f"ufd_{name}_k"], g[f"ufd_{name}_cfg"], g[f"ufd_{name}_y"]
+        up, down, p0, p1 = [int(v) for v in cfg]
+        for fma in (True, False):
+            mine = OO.upfirdn2d_nchw(x, k, up, down, (p0, p1), fma=fma)
+            assert mine.shape == y.shape, name
+            # summation order differs from F.conv2d: a few ulp of the largest term
+            np.testing.assert_allclose(mine, y, rtol=0, atol=2e-6 * max(1.0, np.abs(y).max()), err_msg=name)
+        n, c, h, w = x.shape
+        dense = OO.upfirdn2d_dense(x.reshape(n * c, h, w), k, up, up, down, down, p0, p1, p0, p1).reshape(y.shape)
+        np.testing.assert_allclose(dense, y, rtol=0, atol=2e-6 * max(1.0, np.abs(y).max()), err_msg=name)
+        # torch restatement used inside the generator oracle
+        t = O.upfirdn2d(torch.from_numpy(x), torch.from_numpy(k), up, down, (p0, p1)).numpy()
+        np.testing.assert_allclose(t, y, rtol=0, atol=2e-6 * max(1.0, np.abs(y).max()), err_msg=name)
+
+
+def test_fused_leaky_relu_oracle_matches_reference_fallback(golden_dir):
+    g = _load(golden_dir, "ops_golden.npz")
+    for name in ("fl2d", "fl4d", "fl4d_big"):
+        x, b, y = g[f"{name}_x"], g[f"{name}_b"], g[f"{name}_y"]
+        np.testing.assert_allclose(OO.fused_leaky_relu(x, b), y, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(O.fused_leaky_relu(torch.from_numpy(x), torch.from_numpy(b)).numpy(), y,
+                                   rtol=1e-6, atol=1e-7)
+
+
+def test_fused_bias_act_grad_modes():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 3, 4, 5)).astype(np.float32)
+    b = rng.standard_normal(3).astype(np.float32)
+    ref = rng.standard_normal(x.shape).astype(np.float32)
+    y1 = OO.fused_bias_act(x, b, ref, 3, 1, 0.2, 1.5)
+    xb = x + b[None, :, None, None]
+    np.testing.assert_allclose(y1, np.where(ref > 0, xb, xb * np.float32(0.2)) * np.float32(1.5), rtol=1e-6)
+    assert not OO.fused_bias_act(x, b, ref, 3, 2, 0.2, 1.5).any()
+    np.testing.assert_allclose(OO.fused_bias_act(x, None, None, 1, 0, 0.2, 2.0), x * 2)
+
+
+@pytest.mark.parametrize("fname", ["generator_g32.npz", "generator_g128.npz"])
+def test_generator_oracle_matches_reference(golden_dir, fname):
+    g = _load(golden_dir, fname)
+    size, cm, seed = int(g["size"]), int(g["cm"]), int(g["seed"])
+    sd = O.synth_state_dict(size, channel_multiplier=cm, seed=seed)
+    _, num_layers, _ = O.layout(size)
+    noise = [torch.from_numpy(g[f"noise_{l}"]) if f"noise_{l}" in g.files else None for l in range(num_layers)]
+    with torch.no_grad():
+        w = O.mapping(torch.from_numpy(g["z"]), sd)
+        np.testing.assert_allclose(w.numpy(), g["w"], rtol=1e-4, atol=1e-5)
+        image, acts = O.generator_forward(sd, size, torch.from_numpy(g["latent"]), noise, torch.from_numpy(g["psi"]),
+                                          torch.from_numpy(g["truncation_latent"]), channel_multiplier=cm)
+    scale = np.abs(g["image"]).max()
+    assert np.abs(image.numpy() - g["image"]).max() <= 2e-5 * scale
+    from tests.golden.make_golden import strided
+
+    for l, a in enumerate(acts):
+        ref = g[f"act_{l}"]
+        assert np.abs(strided(a) - ref).max() <= 2e-5 * float(g[f"act_{l}_absmax"]), l
