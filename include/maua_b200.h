@@ -1,0 +1,179 @@
+/*
+ * maua_b200.h — C ABI of libmaua_b200.so: the sm_100a synthesis hot path of the audio-reactive StyleGAN2
+ * pipeline (drop-in for the native side of JCBrouwer/maua-stylegan2's `op/` extensions and the
+ * `models/stylegan2.py:Generator` forward).
+ *
+ * Conventions (every entry point):
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream); all work is asynchronous
+ *     on that stream, nothing synchronises, nothing allocates device memory (the caller owns every buffer;
+ *     reference ownership rule: inputs borrowed, outputs caller-allocated — SURVEY.md §8(b) "Op ABI");
+ *   - return value 0 = success, negative = error (MAUA_E_*); never throws across the ABI;
+ *     `maua_last_error()` returns a thread-local human-readable message for the last failure.
+ *   - all tensors are dense fp32 unless stated; NCHW unless the name says nhwc.
+ *
+ * Reference interfaces replaced (file:line in /root/reference):
+ *   maua_upfirdn2d_f32        <- torch::Tensor upfirdn2d(input,kernel,up_x,up_y,down_x,down_y,pad_x0,pad_x1,pad_y0,pad_y1)
+ *                                op/upfirdn2d.cpp:12-23, kernel op/upfirdn2d_kernel.cu:49-207
+ *   maua_fused_bias_act_f32   <- torch::Tensor fused_bias_act(input,bias,refer,act,grad,alpha,scale)
+ *                                op/fused_bias_act.cpp:11-21, kernel op/fused_bias_act_kernel.cu:18-49
+ *   maua_linear_f32           <- EqualLinear.forward                      models/stylegan2.py:140-146
+ *   maua_style_prologue_f32   <- truncation lerp + modulation EqualLinear + demod coefficients
+ *                                models/stylegan2.py:541-543, :220-225
+ *   maua_modconv_simt_f32     <- ModulatedConv2d.forward (fp32 SIMT, exact-order fallback) models/stylegan2.py:217-254
+ *   maua_modconv_tc           <- ModulatedConv2d.forward (tcgen05 tensor-core path)       models/stylegan2.py:217-254
+ *   maua_blur_act_nhwc        <- Blur.forward + NoiseInjection + FusedLeakyReLU           models/stylegan2.py:89-92,262-266
+ *   maua_noise_bias_act_f32   <- NoiseInjection.forward + FusedLeakyReLU.forward models/stylegan2.py:262-266, op/fused_act.py:82-97
+ *   maua_torgb_f32            <- ToRGB.forward (1x1 modconv + bias + Upsample(skip))      models/stylegan2.py:356-365
+ *   maua_rgb_to_u8_nhwc       <- render.split_batches clamp/scale/permute/astype(uint8)   render.py:40-43
+ */
+#ifndef MAUA_B200_H
+#define MAUA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAUA_OK 0
+#define MAUA_E_ARG (-1)      /* invalid argument / unsupported shape */
+#define MAUA_E_CUDA (-2)     /* CUDA runtime / driver error (launch, tensor-map encode, ...) */
+#define MAUA_E_UNSUPPORTED (-3)
+
+#define MAUA_ABI_VERSION 1
+
+int maua_abi_version(void);
+const char* maua_last_error(void);
+/* Number of kernels launched through this library by the calling process (bench.py's gpu_launches). */
+long long maua_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Operator ABI (reference op/ extensions)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* x: [major, in_h, in_w, minor]  ->  y: [major, out_h, out_w, minor],
+ * out = (in*up + pad0 + pad1 - k + down) / down  (op/upfirdn2d_kernel.cu:237-240); k: [kh, kw] (un-flipped).
+ * Accumulation order per output is y-major / x-minor fp32 FMA, identical to the reference kernels. */
+int maua_upfirdn2d_f32(const float* x, float* y, const float* k, int major, int in_h, int in_w, int minor, int kh,
+                       int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0,
+                       int pad_y1, void* stream);
+
+/* y[i] = act(x[i] + b[(i / step_b) % size_b]) * scale;  act: 1 linear, 3 leaky-relu(alpha);
+ * grad: 0 forward, 1 gated by ref, 2 zeros.  b / ref may be NULL (size_b = 0). */
+int maua_fused_bias_act_f32(const float* x, const float* b, const float* ref, float* y, long long n, int step_b,
+                            int size_b, int act, int grad, float alpha, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Style / mapping
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* y[b,n] = act( sum_k x[b,k] * w[n,k] * w_scale + bias[n] * bias_scale );  act 0: none, 1: lrelu(0.2)*sqrt(2).
+ * pixel_norm != 0 first normalises each row of x: x * rsqrt(mean(x^2) + 1e-8) (models/stylegan2.py:15-20). */
+int maua_linear_f32(const float* x, const float* w, const float* bias, float* y, int batch, int in_dim, int out_dim,
+                    float w_scale, float bias_scale, int act, int pixel_norm, void* stream);
+
+/* One modulated layer of the style prologue.  All pointers are device pointers. */
+typedef struct MauaStyleJob {
+  const float* mod_w; /* [cin, style_dim]  conv.modulation.weight */
+  const float* mod_b; /* [cin]             conv.modulation.bias   */
+  const float* wsq;   /* [cout, cin] = w_scale^2 * sum_k W^2, or NULL when demodulate=False */
+  float* s_out;       /* [batch, cin]  */
+  float* d_out;       /* [batch, cout] (ignored when wsq == NULL) */
+  int32_t cin;
+  int32_t cout;
+  int32_t latent_index; /* which W+ row feeds this layer */
+  int32_t reserved;
+} MauaStyleJob;
+
+/* For every job j and sample b:
+ *   w      = mean[:] + psi[b] * (latent[b, jobs[j].latent_index, :] - mean[:])      (psi NULL -> psi_scalar)
+ *   s[b,:] = w @ (mod_w / sqrt(style_dim))^T + mod_b
+ *   d[b,:] = rsqrt( sum_ci s[b,ci]^2 * wsq[:,ci] + 1e-8 )
+ * `jobs` is a DEVICE array of n_jobs MauaStyleJob.  latent: [batch, n_latent, style_dim]; mean: [style_dim] or NULL
+ * (NULL = no truncation).  latent_trunc_out (may be NULL): [batch, n_latent, style_dim] truncated latents. */
+int maua_style_prologue_f32(const MauaStyleJob* jobs, int n_jobs, const float* latent, const float* mean,
+                            const float* psi, float psi_scalar, float* latent_trunc_out, int batch, int n_latent,
+                            int style_dim, void* stream);
+
+/* wsq[co,ci] = w_scale^2 * sum_{ky,kx} w[co,ci,ky,kx]^2   (w: [cout,cin,k,k]) */
+int maua_weight_sq_f32(const float* w, float* wsq, int cout, int cin, int ksize, float w_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * fp32 SIMT path (exact-order fallback; also the generic path for arbitrary shapes)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* y[b,co] = d[b,co] * sum_{ci,ky,kx} w_scale*w[co,ci,ky,kx] * s[b,ci] * x[b,ci, ...]
+ *   up == 0: same-resolution, zero padding ksize/2                      -> y [B,Cout,H,W]
+ *   up == 1: stride-2 transposed conv, no padding (ksize must be 3)      -> y [B,Cout,2H+1,2W+1]
+ * s may be NULL (== 1), d may be NULL (== 1). */
+int maua_modconv_simt_f32(const float* x, const float* w, const float* s, const float* d, float* y, int batch,
+                          int cin, int cout, int h, int w_, int ksize, int up, float w_scale, void* stream);
+
+/* y = lrelu( (x + noise_weight[0] * noise[b*noise_bstride + pix]) + bias[c], slope ) * scale
+ * noise may be NULL; noise_bstride is 0 for a broadcast [1,1,H,W] buffer, H*W for per-sample noise. */
+int maua_noise_bias_act_f32(const float* x, const float* noise, const float* noise_weight, const float* bias,
+                            float* y, int batch, int ch, int h, int w, long long noise_bstride, float slope,
+                            float scale, void* stream);
+
+/* rgb[b,r] = sum_c (w_scale * wrgb[r,c] * s[b,c]) * x[b,c] + bias[r] + upfirdn2d(skip, k4, up=2, pad=(2,1))[b,r]
+ * skip: [B,3,H/2,W/2] or NULL;  k4: [4,4] FIR (upsample.kernel buffer). */
+int maua_torgb_f32(const float* x, const float* wrgb, const float* s, const float* bias, const float* skip,
+                   const float* k4, float* y, int batch, int cin, int h, int w, float w_scale, void* stream);
+
+/* out[b,y,x,c] = (uint8) trunc( (clamp(rgb[b,c,y,x], -1, 1) + 1) * 127.5 ) */
+int maua_rgb_to_u8_nhwc(const float* rgb, uint8_t* out, int batch, int h, int w, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Tensor-core path (tcgen05 / TMEM / TMA), NHWC split-bf16 activations
+ *
+ * Activations between layers are stored channels-last as TWO bf16 planes (hi, lo) with hi + lo ~= fp32 value
+ * (16 mantissa bits), already multiplied by the consuming layer's style s[b,ci]; weights are packed once as
+ * [tap][cout][cin] bf16 hi/lo with w_scale folded in.  The conv evaluates hi*hi + hi*lo + lo*hi on the tensor
+ * cores with fp32 accumulation in TMEM (n_products = 3, |err| ~ 2^-16 rel) or hi*hi only (n_products = 1).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* w [cout,cin,k,k] fp32 -> w_hi / w_lo [k*k][cout][cin] bf16 (value = w * w_scale). */
+int maua_pack_weight_bf16x2(const float* w, void* w_hi, void* w_lo, int cout, int cin, int ksize, float w_scale,
+                            void* stream);
+
+/* x [B,C,H,W] fp32 (x_bstride = 0 broadcasts one sample, e.g. the constant input) times s[b,c]
+ * -> x_hi / x_lo [B,H,W,C] bf16. s may be NULL. */
+int maua_modulate_split_nhwc(const float* x, long long x_bstride, const float* s, void* x_hi, void* x_lo, int batch,
+                             int ch, int h, int w, void* stream);
+
+typedef struct MauaConvEpilogue {
+  const float* d;            /* [B,Cout] demod or NULL                                                    */
+  const float* noise;        /* [B or 1, H_out, W_out] or NULL                                            */
+  const float* noise_weight; /* device scalar                                                             */
+  const float* bias;         /* [Cout] or NULL                                                            */
+  const float* s_next;       /* [B,Cout] style of the consuming layer (applied before the split) or NULL  */
+  void* out_hi;              /* [B,H_out,W_out,Cout] bf16 or NULL                                         */
+  void* out_lo;              /*  "                                                                         */
+  float* out_f32_nchw;       /* [B,Cout,H_out,W_out] post-activation fp32 or NULL                         */
+  float* out_raw_nhwc;       /* up==1 only: [B,2H+1,2W+1,Cout] fp32 = d * convT(x) (pre-blur)             */
+  long long noise_bstride;   /* 0 or H_out*W_out                                                          */
+  float slope;               /* leaky-relu slope (0.2)                                                    */
+  float act_scale;           /* sqrt(2)                                                                   */
+  int32_t activate;          /* 0: linear (no noise/bias/act), 1: noise+bias+lrelu                        */
+  int32_t reserved;
+} MauaConvEpilogue;
+
+/* 3x3 modulated conv on the tensor cores.  x_hi/x_lo [B,H,W,Cin] bf16 (pre-scaled by s), w_hi/w_lo [9][Cout][Cin].
+ *   up == 0: same resolution, zero pad 1, fused epilogue (demod, noise, bias, lrelu, next-style, split)
+ *   up == 1: stride-2 transposed conv evaluated as 4 sub-pixel phases; writes ep->out_raw_nhwc (demod applied).
+ * Requirements: Cin % 32 == 0, Cout % 16 == 0, Cout >= 16.  `ep` is a HOST pointer (copied at launch). */
+int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                    const MauaConvEpilogue* ep_host, int batch, int cin, int cout, int h, int w, int up,
+                    int n_products, void* stream);
+
+/* u [B,Hu,Wu,C] fp32 (Hu = 2H+1) -> 4x4 FIR k4 with pad (1,1) -> [B,Hu-1,Wu-1,C], then the activation
+ * epilogue of `ep` (noise, bias, lrelu, s_next, split / fp32 NCHW).  ep->d is ignored (already applied). */
+int maua_blur_act_nhwc(const float* u, const float* k4, const MauaConvEpilogue* ep_host, int batch, int ch, int hu,
+                       int wu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAUA_B200_H */

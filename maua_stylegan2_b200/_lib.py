@@ -1,0 +1,96 @@
+"""ctypes binding of libmaua_b200.so (include/maua_b200.h).  Fails loudly when the library is missing:
+there is NO CPU / eager fallback for CUDA tensors anywhere in this package."""
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmaua_b200.so")
+
+
+class MauaError(RuntimeError):
+    pass
+
+
+class StyleJob(C.Structure):
+    """MauaStyleJob (include/maua_b200.h)."""
+    _fields_ = [("mod_w", C.c_void_p), ("mod_b", C.c_void_p), ("wsq", C.c_void_p), ("s_out", C.c_void_p),
+                ("d_out", C.c_void_p), ("cin", C.c_int32), ("cout", C.c_int32), ("latent_index", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class ConvEpilogue(C.Structure):
+    """MauaConvEpilogue (include/maua_b200.h)."""
+    _fields_ = [("d", C.c_void_p), ("noise", C.c_void_p), ("noise_weight", C.c_void_p), ("bias", C.c_void_p),
+                ("s_next", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_f32_nchw", C.c_void_p),
+                ("out_raw_nhwc", C.c_void_p), ("noise_bstride", C.c_longlong), ("slope", C.c_float),
+                ("act_scale", C.c_float), ("activate", C.c_int32), ("reserved", C.c_int32)]
+
+
+_p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> argtypes; every function returns int (0 ok / negative error) unless listed in _SPECIAL
+SIGNATURES = {
+    "maua_upfirdn2d_f32": [_p, _p, _p] + [_i] * 14 + [_p],
+    "maua_fused_bias_act_f32": [_p, _p, _p, _p, _ll, _i, _i, _i, _i, _f, _f, _p],
+    "maua_linear_f32": [_p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _i, _p],
+    "maua_style_prologue_f32": [_p, _i, _p, _p, _p, _f, _p, _i, _i, _i, _p],
+    "maua_weight_sq_f32": [_p, _p, _i, _i, _i, _f, _p],
+    "maua_modconv_simt_f32": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p],
+    "maua_noise_bias_act_f32": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _ll, _f, _f, _p],
+    "maua_torgb_f32": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p],
+    "maua_rgb_to_u8_nhwc": [_p, _p, _i, _i, _i, _p],
+    "maua_pack_weight_bf16x2": [_p, _p, _p, _i, _i, _i, _f, _p],
+    "maua_modulate_split_nhwc": [_p, _ll, _p, _p, _p, _i, _i, _i, _i, _p],
+    "maua_modconv_tc": [_p, _p, _p, _p, C.POINTER(ConvEpilogue), _i, _i, _i, _i, _i, _i, _i, _p],
+    "maua_blur_act_nhwc": [_p, _p, C.POINTER(ConvEpilogue), _i, _i, _i, _i, _p],
+}
+_SPECIAL = {
+    "maua_abi_version": (C.c_int, []),
+    "maua_last_error": (C.c_char_p, []),
+    "maua_launch_count": (C.c_longlong, []),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MauaError(f"{LIB_PATH} is missing: run `python -m maua_stylegan2_b200.build` "
+                            "(or __graft_entry__.build()); there is no fallback path")
+        handle = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        for name, (res, argtypes) in _SPECIAL.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = res
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise MauaError(f"{what} failed (rc={rc}): {lib().maua_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count():
+    return int(lib().maua_launch_count())
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)

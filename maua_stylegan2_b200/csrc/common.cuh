@@ -1,0 +1,66 @@
+// Shared host/device helpers for libmaua_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/maua_b200.h"
+
+namespace maua {
+
+// thread-local error text + process-wide launch counter (defined in common.cu)
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define MAUA_CHECK_ARG(cond, ...)            \
+  do {                                       \
+    if (!(cond)) {                           \
+      ::maua::set_error(__VA_ARGS__);        \
+      return MAUA_E_ARG;                     \
+    }                                        \
+  } while (0)
+
+// Checks the launch (not the execution: everything is asynchronous on the caller's stream).
+#define MAUA_CHECK_LAUNCH(name)                                                       \
+  do {                                                                                \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess) {                                                          \
+      ::maua::set_error("%s: launch failed: %s", name, cudaGetErrorString(_e));       \
+      return MAUA_E_CUDA;                                                             \
+    }                                                                                 \
+    ::maua::count_launch();                                                           \
+  } while (0)
+
+#define MAUA_CHECK_CUDA(expr)                                                         \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      ::maua::set_error("%s failed: %s", #expr, cudaGetErrorString(_e));              \
+      return MAUA_E_CUDA;                                                             \
+    }                                                                                 \
+  } while (0)
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) {
+  return (a + b - 1) / b;
+}
+
+__host__ __device__ __forceinline__ int floor_div(int a, int b) {
+  int q = a / b;
+  return (q * b > a) ? q - 1 : q;
+}
+
+// fp32 -> (hi, lo) bf16 pair with hi + lo == x up to 2^-17 relative.
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ float lrelu_scaled(float v, float slope, float scale) {
+  return __fmul_rn(v > 0.f ? v : __fmul_rn(v, slope), scale);
+}
+
+}  // namespace maua

@@ -1,0 +1,422 @@
+// ModulatedConv2d (3x3) on the 5th-generation tensor cores: TMA -> shared memory -> tcgen05.mma -> TMEM -> epilogue.
+//
+// Reference path replaced: models/stylegan2.py:217-254 (per-sample weight modulation + cuDNN grouped conv /
+// grouped transposed conv) + :262-266 (noise) + op/fused_act.py:82-97 (bias + leaky ReLU).
+//
+// Formulation:  o[b,co,p] = d[b,co] * sum_{tap,ci} Wc[tap][co][ci] * (s[b,ci]*x[b,ci,p+tap])
+//   - the style s is already folded into the activation operand by the producing kernel, so the weight operand
+//     is shared by the whole batch and only d (per sample, per output channel) remains for the epilogue;
+//   - implicit GEMM: M = 128 output pixels (TB x TH x TW block of [batch, y, x]), N = BN output channels,
+//     K = Cin per tap.  For tap (ky,kx) the A tile is ONE 4-D TMA box {KC ch, TW, TH, TB} of the NHWC activation
+//     shifted by (dy,dx); the zero padding of the convolution is the TMA out-of-bounds fill, so there is no
+//     im2col buffer and no halo logic.  B tile = {KC, BN, 1} box of the packed [tap][Cout][Cin] weight.
+//   - precision: operands are (hi, lo) bf16 pairs; the tensor core evaluates hi*hi + hi*lo + lo*hi into one fp32
+//     TMEM accumulator (n_products = 3) => ~2^-16 relative product error, fp32-grade results on the bf16 pipe.
+//   - transposed (up) layers are evaluated as 4 sub-pixel phases with 4 TMEM accumulators; only 4 distinct
+//     shifted A tiles serve the 9 taps (A ring stage is held across the taps that share a shift).
+//
+// Warp roles (192 threads): warp 0 = TMA producer (1 lane), warp 1 = TMEM owner + MMA issuer (1 lane),
+// warps 2-5 = epilogue (tcgen05.ld 32 lanes x 16 columns, demod/noise/bias/lrelu/next-style/split, stores).
+// Two independent mbarrier rings (A tiles, B tiles) + one accumulator-full barrier.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace maua {
+namespace tc {
+
+struct Step {
+  int8_t dy, dx;    // shift of the A tile
+  int8_t a_new;     // 1: this step loads / consumes a new A stage
+  int8_t a_last;    // 1: last step that reads the current A stage
+  int8_t tap;       // ky*3 + kx  (index into the packed weight)
+  int8_t phase;     // TMEM accumulator index (sub-pixel phase for up layers)
+  int8_t pad0, pad1;
+};
+
+// same-resolution: tap (ky,kx) reads x[y+ky-1, x+kx-1]
+// up (stride-2 transposed): u[2y'+py, 2x'+px] += W[ky,kx] * x[y'+dy, x'+dx], py = ky&1, dy = (ky==2 ? -1 : 0)
+__constant__ Step c_steps[2][9] = {
+    {{-1, -1, 1, 1, 0, 0}, {-1, 0, 1, 1, 1, 0}, {-1, 1, 1, 1, 2, 0}, {0, -1, 1, 1, 3, 0}, {0, 0, 1, 1, 4, 0},
+     {0, 1, 1, 1, 5, 0},   {1, -1, 1, 1, 6, 0}, {1, 0, 1, 1, 7, 0},  {1, 1, 1, 1, 8, 0}},
+    {{0, 0, 1, 0, 0, 0},   {0, 0, 0, 0, 1, 1},  {0, 0, 0, 0, 3, 2},  {0, 0, 0, 1, 4, 3},  {0, -1, 1, 0, 2, 0},
+     {0, -1, 0, 1, 5, 2},  {-1, 0, 1, 0, 6, 0}, {-1, 0, 0, 1, 7, 1}, {-1, -1, 1, 1, 8, 0}}};
+
+struct Params {
+  int B, H, W, Cin, Cout;  // input activation dims / channels
+  int GH, GW;              // GEMM pixel grid: (H, W) or (H+1, W+1) for up
+  int TB, TH, TW;          // M tile = TB*TH*TW = 128
+  int tiles_x, tiles_y;
+  int BN, n_tiles;
+  int n_kchunks;
+  int SA, SB;
+  int nprod;
+  uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ float lrelu_s(float v, float slope, float scale) {
+  return (v > 0.f ? v : v * slope) * scale;
+}
+
+template <int KC, bool UP>
+__global__ void __launch_bounds__(192, 1)
+modconv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                  const Params p, const MauaConvEpilogue ep) {
+  using namespace ptx;
+  constexpr uint32_t ROW_BYTES = KC * 2;               // one swizzle span per operand row
+  constexpr uint32_t A_HALF = 128 * ROW_BYTES;         // one bf16 plane of the A tile
+  constexpr uint32_t A_STAGE = 2 * A_HALF;             // hi + lo
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+  const uint32_t b_half = (uint32_t)p.BN * ROW_BYTES;
+  const uint32_t b_stage = 2 * b_half;
+  const uint32_t a_base = smem0;
+  const uint32_t b_base = a_base + (uint32_t)p.SA * A_STAGE;
+  const uint32_t bar_base = b_base + (uint32_t)p.SB * b_stage;
+  // barrier slots (8 B each): a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], acc_full, tmem_ptr
+  const uint32_t a_full = bar_base, a_empty = a_full + 8 * p.SA;
+  const uint32_t b_full = a_empty + 8 * p.SA, b_empty = b_full + 8 * p.SB;
+  const uint32_t acc_full = b_empty + 8 * p.SB;
+  const uint32_t tmem_slot = acc_full + 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile coordinates ------------------------------------------------------------------------------------------
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_tile = blockIdx.x / p.n_tiles;
+  const int tile_x = m_tile % p.tiles_x;
+  const int tile_y = (m_tile / p.tiles_x) % p.tiles_y;
+  const int tile_b = m_tile / (p.tiles_x * p.tiles_y);
+  const int x0 = tile_x * p.TW, y0 = tile_y * p.TH, b0 = tile_b * p.TB, n0 = n_tile * p.BN;
+
+  // ---- one-time setup --------------------------------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a_hi);
+    prefetch_tmap(&tm_b_hi);
+    if (p.nprod > 1) {
+      prefetch_tmap(&tm_a_lo);
+      prefetch_tmap(&tm_b_lo);
+    }
+    for (int i = 0; i < p.SA; ++i) {
+      mbar_init(a_full + 8 * i, 1);
+      mbar_init(a_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < p.SB; ++i) {
+      mbar_init(b_full + 8 * i, 1);
+      mbar_init(b_empty + 8 * i, 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const Step* steps = c_steps[UP ? 1 : 0];
+  const uint32_t a_bytes = (p.nprod > 1) ? A_STAGE : A_HALF;
+  const uint32_t b_bytes = (p.nprod > 1) ? b_stage : b_half;
+
+  if (warp == 0 && lane == 0) {
+    // ================================ TMA producer ================================
+    int ia = 0, ib = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int kc = 0; kc < p.n_kchunks; ++kc) {
+      const int c0 = kc * KC;
+#pragma unroll 1
+      for (int st = 0; st < 9; ++st) {
+        const Step s = steps[st];
+        if (s.a_new) {
+          mbar_wait(a_empty + 8 * ia, pa ^ 1);
+          mbar_expect_tx(a_full + 8 * ia, a_bytes);
+          const uint32_t dst = a_base + ia * A_STAGE;
+          tma_load_4d(dst, &tm_a_hi, a_full + 8 * ia, c0, x0 + s.dx, y0 + s.dy, b0);
+          if (p.nprod > 1) tma_load_4d(dst + A_HALF, &tm_a_lo, a_full + 8 * ia, c0, x0 + s.dx, y0 + s.dy, b0);
+          if (++ia == p.SA) { ia = 0; pa ^= 1; }
+        }
+        mbar_wait(b_empty + 8 * ib, pb ^ 1);
+        mbar_expect_tx(b_full + 8 * ib, b_bytes);
+        const uint32_t dstb = b_base + ib * b_stage;
+        tma_load_3d(dstb, &tm_b_hi, b_full + 8 * ib, c0, n0, s.tap);
+        if (p.nprod > 1) tma_load_3d(dstb + b_half, &tm_b_lo, b_full + 8 * ib, c0, n0, s.tap);
+        if (++ib == p.SB) { ib = 0; pb ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================================ MMA issuer ================================
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN);
+    int ia = 0, ib = 0, cur_a = 0;
+    uint32_t pa = 0, pb = 0, started = 0;
+    for (int kc = 0; kc < p.n_kchunks; ++kc) {
+#pragma unroll 1
+      for (int st = 0; st < 9; ++st) {
+        const Step s = steps[st];
+        if (s.a_new) {
+          cur_a = ia;
+          mbar_wait(a_full + 8 * ia, pa);
+          if (++ia == p.SA) { ia = 0; pa ^= 1; }
+        }
+        mbar_wait(b_full + 8 * ib, pb);
+        tc_fence_after();
+        const uint32_t a_hi = a_base + cur_a * A_STAGE, a_lo = a_hi + A_HALF;
+        const uint32_t b_hi = b_base + ib * b_stage, b_lo = b_hi + b_half;
+        const uint32_t acc = tmem_base + (uint32_t)s.phase * (uint32_t)p.BN;
+        uint32_t accumulate = (started >> s.phase) & 1u;
+#pragma unroll 1
+        for (int prod = 0; prod < p.nprod; ++prod) {
+          const uint64_t da = make_kmajor_desc(prod == 2 ? a_lo : a_hi, ROW_BYTES);
+          const uint64_t db = make_kmajor_desc(prod == 1 ? b_lo : b_hi, ROW_BYTES);
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k) {
+            // advancing K by 16 bf16 = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
+            umma_bf16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
+            accumulate = 1;
+          }
+        }
+        started |= 1u << s.phase;
+        umma_commit(b_empty + 8 * ib);
+        if (s.a_last) umma_commit(a_empty + 8 * cur_a);
+        if (++ib == p.SB) { ib = 0; pb ^= 1; }
+      }
+    }
+    umma_commit(acc_full);
+  } else if (warp >= 2) {
+    // ================================ epilogue ================================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int m = quad * 32 + lane;
+    const int tx = m % p.TW, ty = (m / p.TW) % p.TH, tb = m / (p.TW * p.TH);
+    const int gx = x0 + tx, gy = y0 + ty, b = b0 + tb;
+    const bool in_grid = (b < p.B) && (gy < p.GH) && (gx < p.GW);
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    constexpr int NPH = UP ? 4 : 1;
+    const int bc = in_grid ? b : 0;
+    const float* dptr = ep.d ? ep.d + (long long)bc * p.Cout + n0 : nullptr;
+#pragma unroll 1
+    for (int ph = 0; ph < NPH; ++ph) {
+      int oy, ox, OH, OW;
+      bool valid;
+      if (UP) {
+        OH = 2 * p.H + 1; OW = 2 * p.W + 1;
+        oy = 2 * gy + (ph >> 1); ox = 2 * gx + (ph & 1);
+        valid = in_grid && oy < OH && ox < OW;
+      } else {
+        OH = p.H; OW = p.W; oy = gy; ox = gx; valid = in_grid;
+      }
+      const long long pix = valid ? (((long long)b * OH + oy) * OW + ox) : 0;
+      float nz = 0.f;
+      if (!UP && ep.activate && ep.noise && valid)
+        nz = __ldg(ep.noise_weight) * __ldg(ep.noise + (long long)b * ep.noise_bstride + (long long)oy * OW + ox);
+#pragma unroll 1
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t r[16];
+        tmem_ld_x16(lane_addr + (uint32_t)(ph * p.BN + c), r);
+        tmem_ld_wait();
+        if (!valid) continue;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] = __uint_as_float(r[i]);
+          if (dptr) v[i] *= __ldg(dptr + c + i);
+        }
+        if (UP) {
+          float4* dst = reinterpret_cast<float4*>(ep.out_raw_nhwc + pix * p.Cout + n0 + c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          if (ep.activate) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float bb = ep.bias ? __ldg(ep.bias + n0 + c + i) : 0.f;
+              v[i] = lrelu_s((v[i] + nz) + bb, ep.slope, ep.act_scale);
+            }
+          }
+          if (ep.out_f32_nchw) {
+            float* dst = ep.out_f32_nchw + (((long long)b * p.Cout + n0 + c) * OH + oy) * OW + ox;
+            const long long plane = (long long)OH * OW;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[i * plane] = v[i];
+          }
+          if (ep.out_hi) {
+            __nv_bfloat16 h[16], l[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float sv = ep.s_next ? __ldg(ep.s_next + (long long)b * p.Cout + n0 + c + i) : 1.f;
+              split_bf16(v[i] * sv, h[i], l[i]);
+            }
+            uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_hi) + pix * p.Cout + n0 + c);
+            uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_lo) + pix * p.Cout + n0 + c);
+            dh[0] = reinterpret_cast<const uint4*>(h)[0];
+            dh[1] = reinterpret_cast<const uint4*>(h)[1];
+            dl[0] = reinterpret_cast<const uint4*>(l)[0];
+            dl[1] = reinterpret_cast<const uint4*>(l)[1];
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown --------------------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static int encode_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                       const cuuint32_t* box, int row_bytes) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return MAUA_E_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return MAUA_E_CUDA;
+  }
+  return MAUA_OK;
+}
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace tc
+}  // namespace maua
+
+extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                               const MauaConvEpilogue* ep_host, int batch, int cin, int cout, int h, int w, int up,
+                               int n_products, void* stream) {
+  using namespace maua;
+  using namespace maua::tc;
+  MAUA_CHECK_ARG(x_hi && w_hi && ep_host, "modconv_tc: null pointer");
+  MAUA_CHECK_ARG(n_products == 1 || n_products == 3, "modconv_tc: n_products must be 1 or 3");
+  MAUA_CHECK_ARG(n_products == 1 || (x_lo && w_lo), "modconv_tc: lo planes required for n_products == 3");
+  MAUA_CHECK_ARG(batch >= 0 && h >= 1 && w >= 1, "modconv_tc: bad shape");
+  MAUA_CHECK_ARG(cin % 32 == 0 && cin >= 32, "modconv_tc: Cin must be a multiple of 32");
+  MAUA_CHECK_ARG(cout % 16 == 0 && cout >= 16, "modconv_tc: Cout must be a multiple of 16");
+  const MauaConvEpilogue& ep = *ep_host;
+  if (up) {
+    MAUA_CHECK_ARG(ep.out_raw_nhwc, "modconv_tc(up): out_raw_nhwc required");
+  } else {
+    MAUA_CHECK_ARG(ep.out_f32_nchw || ep.out_hi, "modconv_tc: no output requested");
+    MAUA_CHECK_ARG((ep.out_hi != nullptr) == (ep.out_lo != nullptr), "modconv_tc: hi/lo outputs must come in pairs");
+    MAUA_CHECK_ARG(!ep.noise || ep.noise_weight, "modconv_tc: noise without noise_weight");
+  }
+  if (batch == 0) return MAUA_OK;
+
+  Params p;
+  p.B = batch; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout;
+  p.GH = up ? h + 1 : h;
+  p.GW = up ? w + 1 : w;
+  p.TW = next_pow2(p.GW) < 16 ? next_pow2(p.GW) : 16;
+  int th = 128 / p.TW;
+  if (next_pow2(p.GH) < th) th = next_pow2(p.GH);
+  p.TH = th;
+  p.TB = 128 / (p.TW * p.TH);
+  p.tiles_x = ceil_div(p.GW, p.TW);
+  p.tiles_y = ceil_div(p.GH, p.TH);
+  const int tiles_b = ceil_div(batch, p.TB);
+  const long long m_tiles = (long long)p.tiles_x * p.tiles_y * tiles_b;
+  const int kc = (cin % 64 == 0) ? 64 : 32;
+  p.n_kchunks = cin / kc;
+  p.nprod = n_products;
+  const int nphase = up ? 4 : 1;
+  // N tile: largest power-of-two divisor of Cout that fits TMEM (512 columns over all phases); shrink while the
+  // grid would leave SMs idle (keeps at least 64 columns so the MMA stays reasonably efficient)
+  int bn = 16;
+  for (int c = 256; c >= 16; c >>= 1)
+    if (cout % c == 0 && c * nphase <= 512) { bn = c; break; }
+  while (bn > 64 && m_tiles * (cout / bn) < 148 && cout % (bn / 2) == 0) bn >>= 1;
+  p.BN = bn;
+  p.n_tiles = cout / bn;
+  int cols = 32;
+  while (cols < bn * nphase) cols <<= 1;
+  p.tmem_cols = (uint32_t)cols;
+  const int a_stage = 2 * 128 * kc * 2, b_stage = 2 * bn * kc * 2;
+  // short-K layers (high resolution, few channels) are latency-bound per CTA: keep the ring small enough that
+  // several CTAs co-reside on an SM and overlap each other's prologue / epilogue with MMA work
+  const int ctas_per_sm = (p.n_kchunks <= 2) ? 4 : (p.n_kchunks <= 4 ? 2 : 1);
+  int stages = ((216 * 1024) / ctas_per_sm - 2048) / (a_stage + b_stage);
+  if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
+  p.SA = stages;
+  p.SB = stages;
+  const size_t smem = (size_t)stages * (a_stage + b_stage) + 8 * (2 * p.SA + 2 * p.SB + 2) + 1024;
+  MAUA_CHECK_ARG(smem <= 227 * 1024, "modconv_tc: shared memory budget exceeded");
+  MAUA_CHECK_ARG(m_tiles * p.n_tiles < (1LL << 31), "modconv_tc: grid too large");
+
+  // tensor maps: activations [B,H,W,Cin] (dims innermost first), weights [9][Cout][Cin]
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  const cuuint64_t adims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+  const cuuint64_t astr[3] = {(cuuint64_t)cin * 2, (cuuint64_t)w * cin * 2, (cuuint64_t)h * w * cin * 2};
+  const cuuint32_t abox[4] = {(cuuint32_t)kc, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TB};
+  const cuuint64_t bdims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
+  const cuuint64_t bstr[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
+  const cuuint32_t bbox[3] = {(cuuint32_t)kc, (cuuint32_t)bn, 1};
+  int rc;
+  if ((rc = encode_bf16(&ta_hi, x_hi, 4, adims, astr, abox, kc * 2)) != MAUA_OK) return rc;
+  if ((rc = encode_bf16(&tb_hi, w_hi, 3, bdims, bstr, bbox, kc * 2)) != MAUA_OK) return rc;
+  if (n_products > 1) {
+    if ((rc = encode_bf16(&ta_lo, x_lo, 4, adims, astr, abox, kc * 2)) != MAUA_OK) return rc;
+    if ((rc = encode_bf16(&tb_lo, w_lo, 3, bdims, bstr, bbox, kc * 2)) != MAUA_OK) return rc;
+  } else {
+    ta_lo = ta_hi;
+    tb_lo = tb_hi;
+  }
+
+  cudaStream_t st = as_stream(stream);
+  const unsigned grid = (unsigned)(m_tiles * p.n_tiles);
+#define MAUA_TC_LAUNCH(KCV, UPV)                                                                                   \
+  do {                                                                                                             \
+    MAUA_CHECK_CUDA(cudaFuncSetAttribute(modconv_tc_kernel<KCV, UPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                                              \
+    modconv_tc_kernel<KCV, UPV><<<grid, 192, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep);                       \
+  } while (0)
+  if (kc == 64) {
+    if (up) MAUA_TC_LAUNCH(64, true); else MAUA_TC_LAUNCH(64, false);
+  } else {
+    if (up) MAUA_TC_LAUNCH(32, true); else MAUA_TC_LAUNCH(32, false);
+  }
+#undef MAUA_TC_LAUNCH
+  MAUA_CHECK_LAUNCH("modconv_tc");
+  return MAUA_OK;
+}

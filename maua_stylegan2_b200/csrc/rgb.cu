@@ -1,0 +1,148 @@
+// ToRGB (models/stylegan2.py:356-365) and the frame -> bytes conversion (render.py:40-43).  HBM-bound.
+//
+//   torgb_kernel: rgb[b,r,p] = sum_c (c*Wrgb[r,c]*s[b,c]) * x[b,c,p] + bias[r] + up2(skip)[b,r,p]
+//     - the 1x1 modulated conv has no demodulation (models/stylegan2.py:353), so it is a 3-row GEMV per pixel;
+//       the per-sample row vectors live in shared memory, x is streamed once with float4 loads;
+//     - up2 = upfirdn2d(skip, K, up=2, pad=(2,1)) evaluated in place with the reference's polyphase index math
+//       and FMA order (2x2 live taps per output), so no [B,3,H,W] intermediate is written.
+//   rgb_to_u8_kernel: uint8 trunc((clamp(x,-1,1)+1)*127.5), NCHW -> NHWC, 3 B/pixel written.
+#include "common.cuh"
+
+namespace maua {
+
+__device__ __forceinline__ float skip_up2(const float* __restrict__ sp, int sh, int sw, const float* kf, int oy, int ox) {
+  // up=2, pad0=2, 4x4 taps: mid = o - 1, in0 = floor(mid/2), k0 = 2*in0 + 2 - o  
+  const int in0y = floor_div(oy - 1, 2), in0x = floor_div(ox - 1, 2);
+  const int k0y = 2 * in0y + 2 - oy, k0x = 2 * in0x + 2 - ox;
+  float v = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int iy = in0y + a;
+    if (iy < 0 || iy >= sh) continue;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int ix = in0x + e;
+      if (ix < 0 || ix >= sw) continue;
+      v = __fmaf_rn(__ldg(sp + (long long)iy * sw + ix), kf[(3 - (k0y + 2 * a)) * 4 + (3 - (k0x + 2 * e))], v);
+    }
+  }
+  return v;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x, const float* __restrict__ wrgb,
+                                                    const float* __restrict__ s, const float* __restrict__ bias,
+                                                    const float* __restrict__ skip, const float* __restrict__ k4,
+                                                    float* __restrict__ y, int cin, int h, int w, float w_scale) {
+  extern __shared__ float wr[];  // [3][cin]
+  __shared__ float kf[16];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 3 * cin; i += 256) {
+    const int c = i % cin;
+    float v = __ldg(wrgb + i) * w_scale;
+    if (s) v *= __ldg(s + (long long)b * cin + c);
+    wr[i] = v;
+  }
+  if (tid < 16) kf[tid] = k4 ? __ldg(k4 + tid) : 0.f;
+  __syncthreads();
+  const long long hw = (long long)h * w;
+  const long long p0 = (blockIdx.x * 256LL + tid) * VEC;
+  if (p0 >= hw) return;
+  const float* xb = x + (long long)b * cin * hw + p0;
+  float acc[3][VEC];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[r][i] = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < cin; ++c) {
+    float xv[VEC];
+    if (VEC == 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(xb + (long long)c * hw));
+      xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+    } else {
+      xv[0] = __ldg(xb + (long long)c * hw);
+    }
+    const float w0 = wr[c], w1 = wr[cin + c], w2 = wr[2 * cin + c];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      acc[0][i] = fmaf(xv[i], w0, acc[0][i]);
+      acc[1][i] = fmaf(xv[i], w1, acc[1][i]);
+      acc[2][i] = fmaf(xv[i], w2, acc[2][i]);
+    }
+  }
+  const int sh = h >> 1, sw = w >> 1;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float bb = bias ? __ldg(bias + r) : 0.f;
+    float o[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      o[i] = __fadd_rn(acc[r][i], bb);
+      if (skip) {
+        const long long p = p0 + i;
+        const int oy = (int)(p / w), ox = (int)(p - (long long)oy * w);
+        o[i] = __fadd_rn(o[i], skip_up2(skip + ((long long)b * 3 + r) * sh * sw, sh, sw, kf, oy, ox));
+      }
+    }
+    float* yp = y + ((long long)b * 3 + r) * hw + p0;
+    if (VEC == 4) *reinterpret_cast<float4*>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+    else yp[0] = o[0];
+  }
+}
+
+// one thread = one pixel (3 planar loads coalesced across the warp, 3 packed bytes out)
+__global__ void __launch_bounds__(256) rgb_to_u8_kernel(const float* __restrict__ rgb, uint8_t* __restrict__ out,
+                                                        long long hw, long long total) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long b = i / hw, p = i - b * hw;
+    const float* src = rgb + b * 3 * hw + p;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = __ldg(src + c * hw);
+      v = fminf(fmaxf(v, -1.f), 1.f);
+      v = __fmul_rn(__fadd_rn(v, 1.f), 127.5f);
+      out[i * 3 + c] = (uint8_t)(int)v;  // truncation toward zero == numpy astype(uint8) on [0,255]
+    }
+  }
+}
+
+}  // namespace maua
+
+extern "C" int maua_torgb_f32(const float* x, const float* wrgb, const float* s, const float* bias,
+                              const float* skip, const float* k4, float* y, int batch, int cin, int h, int w,
+                              float w_scale, void* stream) {
+  using namespace maua;
+  MAUA_CHECK_ARG(x && wrgb && y && batch >= 0 && cin >= 1 && h >= 1 && w >= 1, "torgb: bad arguments");
+  MAUA_CHECK_ARG(!skip || (k4 && (h % 2 == 0) && (w % 2 == 0)), "torgb: skip needs k4 and even output size");
+  MAUA_CHECK_ARG(cin <= 4096, "torgb: cin too large");
+  if (batch == 0) return MAUA_OK;
+  MAUA_CHECK_ARG(batch <= 65535, "torgb: batch too large");
+  const long long hw = (long long)h * w;
+  cudaStream_t st = as_stream(stream);
+  const size_t smem = 3 * (size_t)cin * sizeof(float);
+  const bool vec = (hw % 4 == 0) && (w % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (vec) {
+    dim3 grid((unsigned)ceil_div(hw / 4, 256LL), batch);
+    torgb_kernel<4><<<grid, 256, smem, st>>>(x, wrgb, s, bias, skip, k4, y, cin, h, w, w_scale);
+  } else {
+    dim3 grid((unsigned)ceil_div(hw, 256LL), batch);
+    torgb_kernel<1><<<grid, 256, smem, st>>>(x, wrgb, s, bias, skip, k4, y, cin, h, w, w_scale);
+  }
+  MAUA_CHECK_LAUNCH("torgb");
+  return MAUA_OK;
+}
+
+extern "C" int maua_rgb_to_u8_nhwc(const float* rgb, uint8_t* out, int batch, int h, int w, void* stream) {
+  using namespace maua;
+  MAUA_CHECK_ARG(rgb && out && batch >= 0 && h >= 1 && w >= 1, "rgb_to_u8: bad arguments");
+  const long long hw = (long long)h * w, total = hw * batch;
+  if (total == 0) return MAUA_OK;
+  long long blocks = ceil_div(total, 256LL);
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  rgb_to_u8_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(rgb, out, hw, total);
+  MAUA_CHECK_LAUNCH("rgb_to_u8");
+  return MAUA_OK;
+}

@@ -1,0 +1,161 @@
+// Style prologue: truncation lerp + all modulation affines + demodulation coefficients in ONE launch,
+// plus the small EqualLinear used by the mapping network.
+//
+// Reference: models/stylegan2.py:541-543 (truncation), :140-146 / :207 (modulation EqualLinear, lr_mul=1,
+// bias_init=1), :220-225 (modulate / demodulate).  The reference materialises the [B,Cout,Cin,k,k] weight
+// tensor per batch; here  d[b,co] = rsqrt( sum_ci s[b,ci]^2 * Wsq[co,ci] + 1e-8 ),  Wsq = c^2 * sum_k W^2
+// (SURVEY.md Appendix B.1), so nothing per-sample is ever written to HBM except s and d.
+#include "common.cuh"
+
+namespace maua {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// grid (n_jobs, batch), 256 threads.  style_dim <= 1024, cin <= 1024.
+__global__ void __launch_bounds__(256) style_prologue_kernel(const MauaStyleJob* __restrict__ jobs,
+                                                             const float* __restrict__ latent,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ psi, float psi_scalar,
+                                                             float* __restrict__ latent_trunc_out, int n_latent,
+                                                             int style_dim) {
+  __shared__ float sw[1024];
+  __shared__ float ss[1024];
+  const MauaStyleJob job = jobs[blockIdx.x];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* lrow = latent + ((long long)b * n_latent + job.latent_index) * style_dim;
+  const float t = psi ? __ldg(psi + b) : psi_scalar;
+  for (int i = tid; i < style_dim; i += 256) {
+    float v = lrow[i];
+    if (mean) {
+      const float m = __ldg(mean + i);
+      v = __fadd_rn(m, __fmul_rn(t, __fsub_rn(v, m)));  // w_bar + psi * (w - w_bar), models/stylegan2.py:541-543
+    }
+    sw[i] = v;
+    if (latent_trunc_out) latent_trunc_out[((long long)b * n_latent + job.latent_index) * style_dim + i] = v;
+  }
+  __syncthreads();
+  const float lin_scale = rsqrtf((float)style_dim);
+  for (int ci = warp; ci < job.cin; ci += 8) {
+    const float* wr = job.mod_w + (long long)ci * style_dim;
+    float acc = 0.f;
+    for (int i = lane; i < style_dim; i += 32) acc = fmaf(sw[i], __ldg(wr + i), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float s = fmaf(acc, lin_scale, __ldg(job.mod_b + ci));
+      ss[ci] = s;
+      job.s_out[(long long)b * job.cin + ci] = s;
+    }
+  }
+  if (job.wsq == nullptr) return;
+  __syncthreads();
+  for (int i = tid; i < job.cin; i += 256) ss[i] = ss[i] * ss[i];
+  __syncthreads();
+  for (int co = warp; co < job.cout; co += 8) {
+    const float* wr = job.wsq + (long long)co * job.cin;
+    float acc = 0.f;
+    for (int i = lane; i < job.cin; i += 32) acc = fmaf(ss[i], __ldg(wr + i), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) job.d_out[(long long)b * job.cout + co] = rsqrtf(acc + 1e-8f);
+  }
+}
+
+// grid (ceil(out_dim/8), batch): one warp per output feature.
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, float* __restrict__ y,
+                                                     int in_dim, int out_dim, float w_scale, float bias_scale,
+                                                     int act, int pixel_norm) {
+  extern __shared__ float sx[];
+  __shared__ float red[8];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* xr = x + (long long)b * in_dim;
+  float sq = 0.f;
+  for (int i = tid; i < in_dim; i += 256) {
+    const float v = xr[i];
+    sx[i] = v;
+    sq = fmaf(v, v, sq);
+  }
+  float norm = 1.f;
+  if (pixel_norm) {
+    sq = warp_sum(sq);
+    if (lane == 0) red[warp] = sq;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    norm = rsqrtf(tot / (float)in_dim + 1e-8f);
+  } else {
+    __syncthreads();
+  }
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= out_dim) return;
+  const float* wr = w + (long long)n * in_dim;
+  float acc = 0.f;
+  for (int i = lane; i < in_dim; i += 32) acc = fmaf(sx[i] * norm, __ldg(wr + i), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float v = acc * w_scale;
+    if (bias) v += __ldg(bias + n) * bias_scale;
+    if (act == 1) v = (v > 0.f ? v : v * 0.2f) * 1.4142135623730951f;
+    y[(long long)b * out_dim + n] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) weight_sq_kernel(const float* __restrict__ w, float* __restrict__ wsq,
+                                                        long long n, int kk, float s2) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float* p = w + i * kk;
+    float acc = 0.f;
+    for (int t = 0; t < kk; ++t) acc = fmaf(p[t], p[t], acc);
+    wsq[i] = acc * s2;
+  }
+}
+
+}  // namespace maua
+
+extern "C" int maua_style_prologue_f32(const MauaStyleJob* jobs, int n_jobs, const float* latent, const float* mean,
+                                       const float* psi, float psi_scalar, float* latent_trunc_out, int batch,
+                                       int n_latent, int style_dim, void* stream) {
+  using namespace maua;
+  MAUA_CHECK_ARG(jobs && latent && n_jobs >= 0 && batch >= 0, "style_prologue: bad arguments");
+  MAUA_CHECK_ARG(style_dim >= 1 && style_dim <= 1024, "style_prologue: style_dim must be in [1,1024]");
+  if (n_jobs == 0 || batch == 0) return MAUA_OK;
+  MAUA_CHECK_ARG(batch <= 65535, "style_prologue: batch too large");
+  style_prologue_kernel<<<dim3(n_jobs, batch), 256, 0, as_stream(stream)>>>(jobs, latent, mean, psi, psi_scalar,
+                                                                           latent_trunc_out, n_latent, style_dim);
+  MAUA_CHECK_LAUNCH("style_prologue");
+  return MAUA_OK;
+}
+
+extern "C" int maua_linear_f32(const float* x, const float* w, const float* bias, float* y, int batch, int in_dim,
+                               int out_dim, float w_scale, float bias_scale, int act, int pixel_norm, void* stream) {
+  using namespace maua;
+  MAUA_CHECK_ARG(x && w && y && batch >= 0 && in_dim >= 1 && out_dim >= 1, "linear: bad arguments");
+  MAUA_CHECK_ARG(in_dim <= 8192, "linear: in_dim > 8192 unsupported");
+  if (batch == 0) return MAUA_OK;
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    const int nb = (batch - b0 < 65535) ? batch - b0 : 65535;
+    linear_kernel<<<dim3(ceil_div(out_dim, 8), nb), 256, in_dim * sizeof(float), as_stream(stream)>>>(
+        x + (long long)b0 * in_dim, w, bias, y + (long long)b0 * out_dim, in_dim, out_dim, w_scale, bias_scale, act,
+        pixel_norm);
+    MAUA_CHECK_LAUNCH("linear");
+  }
+  return MAUA_OK;
+}
+
+extern "C" int maua_weight_sq_f32(const float* w, float* wsq, int cout, int cin, int ksize, float w_scale,
+                                  void* stream) {
+  using namespace maua;
+  MAUA_CHECK_ARG(w && wsq && cout >= 1 && cin >= 1 && ksize >= 1, "weight_sq: bad arguments");
+  const long long n = (long long)cout * cin;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  weight_sq_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(w, wsq, n, ksize * ksize, w_scale * w_scale);
+  MAUA_CHECK_LAUNCH("weight_sq");
+  return MAUA_OK;
+}

@@ -1,0 +1,188 @@
+// upfirdn2d for sm_100a: zero-insert upsample, pad/crop, FIR, decimate — HBM-bound.
+//
+// Replaces the reference kernels op/upfirdn2d_kernel.cu:49-207 behind the ABI of op/upfirdn2d.cpp:12-23.
+// Index semantics (bit-level spec): for output o along one axis
+//     mid = o*down + up - 1 - pad0;  in0 = floor(mid/up);  k0 = (in0+1)*up - mid - 1
+//     out = sum_y sum_x in[in0y+y, in0x+x] * K[kh-1-(k0y+y*up), kw-1-(k0x+x*up)]      (y-major, x-minor, fp32 FMA)
+// Every code path below keeps that accumulation order, so results are bit-identical to the reference CUDA op.
+//
+// Two kernels:
+//   blur_tile_kernel   — identity-rate (up=down=1), taps <= 4x4, minor == 1 (Blur after the up-conv: 96 % of the
+//                        upfirdn2d bytes of a frame).  One CTA = one output tile of one plane; the input tile
+//                        (+3 halo) is staged in shared memory with coalesced loads, every thread produces a
+//                        4 x RY register block from LDS.128 rows and emits float4 stores.
+//   generic_kernel     — everything else (polyphase up/down, large kernels, minor > 1): one thread per output.
+#include "common.cuh"
+
+namespace maua {
+
+struct UfdParams {
+  int major, in_h, in_w, minor, kh, kw;
+  int up_x, up_y, down_x, down_y, px0, py0;
+  int out_h, out_w;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// identity-rate tiled kernel
+// ---------------------------------------------------------------------------------------------------------------
+template <int TW, int RY>
+__global__ void __launch_bounds__(256) blur_tile_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                        const float* __restrict__ k, UfdParams p, int vec_store) {
+  constexpr int TXN = TW / 4;        // threads along x
+  constexpr int TYN = 256 / TXN;     // thread rows
+  constexpr int TH = TYN * RY;       // output rows per tile
+  constexpr int COLS = TW + 4;       // staged input columns (TW + 3 needed)
+  constexpr int PITCH = TW + 8;      // keeps every row 16-byte aligned
+  constexpr int ROWS = TH + 3;
+  __shared__ __align__(16) float sx[ROWS * PITCH];
+  __shared__ float skf[16];  // flipped, zero-padded to 4x4
+
+  const int tid = threadIdx.x;
+  const int tiles_x = (p.out_w + TW - 1) / TW;
+  const int tile_x = blockIdx.x % tiles_x;
+  const int tile_y = blockIdx.x / tiles_x;
+  const int ox0 = tile_x * TW;
+  const int oy0 = tile_y * TH;
+  const int ix0 = ox0 - p.px0;  // up == 1: in0 = o - pad0, k0 = 0
+  const int iy0 = oy0 - p.py0;
+
+  if (tid < 16) {
+    const int ky = tid >> 2, kx = tid & 3;
+    float v = 0.f;
+    if (ky < p.kh && kx < p.kw) v = k[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)];
+    skf[tid] = v;
+  }
+
+  for (long long plane = blockIdx.y; plane < p.major; plane += gridDim.y) {
+    const float* xp = x + plane * (long long)p.in_h * p.in_w;
+    __syncthreads();  // previous iteration's readers are done (also orders skf)
+    for (int idx = tid; idx < ROWS * COLS; idx += 256) {
+      const int r = idx / COLS;
+      const int c = idx - r * COLS;
+      const int iy = iy0 + r, ix = ix0 + c;
+      float v = 0.f;
+      if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) v = __ldg(xp + (long long)iy * p.in_w + ix);
+      sx[r * PITCH + c] = v;
+    }
+    __syncthreads();
+
+    const int tx = tid % TXN;
+    const int ty = tid / TXN;
+    float kf[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) kf[i] = skf[i];
+    float acc[RY][4];
+#pragma unroll
+    for (int j = 0; j < RY; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+
+#pragma unroll
+    for (int r = 0; r < RY + 3; ++r) {
+      const float4 a = *reinterpret_cast<const float4*>(&sx[(ty * RY + r) * PITCH + tx * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sx[(ty * RY + r) * PITCH + tx * 4 + 4]);
+      const float row[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < RY; ++j) {
+        const int ky = r - j;
+        if (ky >= 0 && ky < 4) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) acc[j][i] = __fmaf_rn(row[i + kx], kf[ky * 4 + kx], acc[j][i]);
+        }
+      }
+    }
+
+    float* yp = y + plane * (long long)p.out_h * p.out_w;
+    const int ox = ox0 + tx * 4;
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      const int oy = oy0 + ty * RY + j;
+      if (oy >= p.out_h) continue;
+      float* dst = yp + (long long)oy * p.out_w + ox;
+      if (vec_store && ox + 3 < p.out_w) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (ox + i < p.out_w) dst[i] = acc[j][i];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// generic kernel: one thread per output element (ox fastest, then minor? no: minor fastest as in memory)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) generic_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                      const float* __restrict__ k, UfdParams p, long long total) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    long long t = i;
+    const int m = (int)(t % p.minor);
+    t /= p.minor;
+    const int ox = (int)(t % p.out_w);
+    t /= p.out_w;
+    const int oy = (int)(t % p.out_h);
+    const long long major = t / p.out_h;
+
+    const int mid_y = oy * p.down_y + p.up_y - 1 - p.py0;
+    const int mid_x = ox * p.down_x + p.up_x - 1 - p.px0;
+    const int in0_y = floor_div(mid_y, p.up_y);
+    const int in0_x = floor_div(mid_x, p.up_x);
+    const int k0_y = (in0_y + 1) * p.up_y - mid_y - 1;
+    const int k0_x = (in0_x + 1) * p.up_x - mid_x - 1;
+    const float* xp = x + major * (long long)p.in_h * p.in_w * p.minor + m;
+    float v = 0.f;
+    for (int fy = k0_y, iy = in0_y; fy < p.kh; fy += p.up_y, ++iy) {
+      if (iy < 0 || iy >= p.in_h) continue;
+      const float* krow = k + (p.kh - 1 - fy) * p.kw;
+      const float* xrow = xp + (long long)iy * p.in_w * p.minor;
+      for (int fx = k0_x, ix = in0_x; fx < p.kw; fx += p.up_x, ++ix) {
+        if (ix < 0 || ix >= p.in_w) continue;
+        v = __fmaf_rn(__ldg(xrow + (long long)ix * p.minor), __ldg(krow + (p.kw - 1 - fx)), v);
+      }
+    }
+    y[i] = v;
+  }
+}
+
+}  // namespace maua
+
+extern "C" int maua_upfirdn2d_f32(const float* x, float* y, const float* k, int major, int in_h, int in_w, int minor,
+                                  int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1,
+                                  int pad_y0, int pad_y1, void* stream) {
+  using namespace maua;
+  MAUA_CHECK_ARG(x && y && k, "upfirdn2d: null pointer");
+  MAUA_CHECK_ARG(major >= 0 && in_h >= 1 && in_w >= 1 && minor >= 1 && kh >= 1 && kw >= 1, "upfirdn2d: bad shape");
+  MAUA_CHECK_ARG(up_x >= 1 && up_y >= 1 && down_x >= 1 && down_y >= 1, "upfirdn2d: up/down must be >= 1");
+  UfdParams p;
+  p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kh = kh; p.kw = kw;
+  p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y; p.px0 = pad_x0; p.py0 = pad_y0;
+  p.out_h = (in_h * up_y + pad_y0 + pad_y1 - kh + down_y) / down_y;
+  p.out_w = (in_w * up_x + pad_x0 + pad_x1 - kw + down_x) / down_x;
+  if (major == 0 || p.out_h <= 0 || p.out_w <= 0) return MAUA_OK;
+  cudaStream_t st = as_stream(stream);
+
+  if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && kh <= 4 && kw <= 4 && minor == 1) {
+    const int vec = ((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (p.out_w & 3) == 0) ? 1 : 0;
+    const int planes_y = major < 32768 ? major : 32768;
+    if (p.out_w > 64) {
+      constexpr int TW = 128, RY = 4, TH = (256 / (TW / 4)) * RY;
+      dim3 grid(ceil_div(p.out_w, TW) * ceil_div(p.out_h, TH), planes_y);
+      blur_tile_kernel<TW, RY><<<grid, 256, 0, st>>>(x, y, k, p, vec);
+    } else {
+      constexpr int TW = 32, RY = 2, TH = (256 / (TW / 4)) * RY;
+      dim3 grid(ceil_div(p.out_w, TW) * ceil_div(p.out_h, TH), planes_y);
+      blur_tile_kernel<TW, RY><<<grid, 256, 0, st>>>(x, y, k, p, vec);
+    }
+    MAUA_CHECK_LAUNCH("upfirdn2d(blur_tile)");
+    return MAUA_OK;
+  }
+  const long long total = (long long)major * p.out_h * p.out_w * minor;
+  long long blocks = ceil_div(total, 256LL);
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, k, p, total);
+  MAUA_CHECK_LAUNCH("upfirdn2d(generic)");
+  return MAUA_OK;
+}

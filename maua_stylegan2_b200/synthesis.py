@@ -1,0 +1,152 @@
+"""Orchestration of one Generator forward over the C ABI (the body of models/stylegan2.py:537-576).
+
+Per batch: 1 style-prologue launch, then per StyledConv
+   impl "tc":   [modulate_split if the input is fp32 NCHW]  ->  modconv_tc (epilogue fused)
+                up layers: modconv_tc(up=1) -> blur_act_nhwc
+   impl "simt": modconv_simt -> [upfirdn2d blur] -> noise_bias_act
+and a torgb launch per resolution.  Python bends (`transform_dict_list`) are applied on real fp32 NCHW tensors
+between layers, exactly where the reference applies them (ManipulationLayer, models/stylegan2.py:297-307).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from .plan import batch_buffers
+from .stylegan2 import SQRT2, _modconv_simt, _noise_bias_act, _prep_noise, _torgb, frames_to_u8
+from .op import upfirdn2d
+
+
+def _bend(x, layer_id, bends):
+    for t in bends:
+        if t["layer"] == layer_id:
+            x = t["transform"].to(x.device)(x)
+    return x
+
+
+def _has_bend(layer_id, bends):
+    return any(t["layer"] == layer_id for t in bends)
+
+
+def _modulate_split(x, bstride, s, batch):
+    """fp32 NCHW (optionally batch-broadcast) * s[b,c] -> (hi, lo) bf16 NHWC."""
+    c, h, w = x.shape[1], x.shape[2], x.shape[3]
+    hi = torch.empty((batch, h, w, c), device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    L.call("maua_modulate_split_nhwc", x.data_ptr(), bstride, L.ptr(s), hi.data_ptr(), lo.data_ptr(), batch, c, h, w,
+           L.stream_ptr(x.device))
+    return hi, lo
+
+
+def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=False):
+    device = latent.device
+    batch = latent.shape[0]
+    plan = g._get_plan()
+    with torch.cuda.device(device):
+        bc = batch_buffers(g, plan, batch)
+        stream = L.stream_ptr(device)
+
+        # ---- style prologue: truncation + all affines + demod (models/stylegan2.py:541-543, :220-225) --------------
+        mean = g.truncation_latent.to(device=device, dtype=torch.float32).contiguous()
+        psi_t, psi_s = None, 1.0
+        if torch.is_tensor(truncation):
+            psi_t = truncation.to(device=device, dtype=torch.float32).contiguous()
+            if psi_t.numel() == 1:
+                psi_t = psi_t.reshape(1).expand(batch).contiguous()
+            elif psi_t.numel() != batch:
+                raise L.MauaError(f"truncation has {psi_t.numel()} entries for a batch of {batch}")
+        else:
+            psi_s = float(truncation)
+        latent_t = torch.empty_like(latent)
+        L.call("maua_style_prologue_f32", bc["table"].data_ptr(), plan["n_jobs"], latent.data_ptr(), mean.data_ptr(),
+               L.ptr(psi_t), psi_s, latent_t.data_ptr(), batch, g.n_latent, g.style_dim, stream)
+
+        # ---- input (models/stylegan2.py:547-548) --------------------------------------------------------------------
+        from .stylegan2 import ConstantInput
+
+        if isinstance(g.input, ConstantInput):
+            x = g.input.input
+            x_bstride = 0
+        else:
+            x = g.input(latent_t)
+            x_bstride = x[0].numel()
+        if _has_bend(0, bends):
+            x = _bend(x.expand(batch, -1, -1, -1).contiguous() if x.shape[0] == 1 else x, 0, bends)
+            x_bstride = x[0].numel()
+        split = None  # (hi, lo) bf16 NHWC pre-scaled by the consuming layer's style, when available
+
+        acts = []
+        image = None
+        layers = plan["layers"]
+        nprod = 1 if g.precision == "bf16" else 3
+        current_size = 2  # doubled by every up layer; conv1 runs at 4
+        for li, lp in enumerate(layers):
+            sp = lp.spec
+            conv = sp.mod.conv
+            s, d = bc["views"][lp.job]
+            nxt = layers[li + 1] if li + 1 < len(layers) else None
+            bend_here = _has_bend(sp.layer_id, bends)
+            nz = noise[sp.noise_index]
+            in_h, in_w = (x.shape[2], x.shape[3]) if split is None else (split[0].shape[1], split[0].shape[2])
+            out_h, out_w = (2 * in_h, 2 * in_w) if sp.up else (in_h, in_w)
+            if nz is None:  # randomize_noise=True: fresh N(0,1) per layer (models/stylegan2.py:263-265)
+                nz = torch.randn(batch, 1, out_h, out_w, device=device)
+
+            if lp.tc_ok:
+                if split is None:
+                    split = _modulate_split(x.contiguous(), x_bstride, s, batch)
+                want_split = nxt is not None and nxt.tc_ok and not bend_here
+                want_f32 = want_acts or bend_here or sp.rgb is not None or (nxt is not None and not want_split)
+                y = torch.empty((batch, sp.cout, out_h, out_w), device=device, dtype=torch.float32) if want_f32 else None
+                o_hi = o_lo = None
+                if want_split:
+                    o_hi = torch.empty((batch, out_h, out_w, sp.cout), device=device, dtype=torch.bfloat16)
+                    o_lo = torch.empty_like(o_hi)
+                nzc, nz_bs = _prep_noise(nz, device, batch, out_h * out_w)
+                ep = L.ConvEpilogue()
+                ep.noise, ep.noise_weight, ep.noise_bstride = nzc.data_ptr(), sp.mod.noise.weight.data_ptr(), nz_bs
+                ep.bias = sp.mod.activate.bias.data_ptr()
+                ep.s_next = bc["views"][nxt.job][0].data_ptr() if want_split else None
+                ep.out_hi, ep.out_lo = L.ptr(o_hi), L.ptr(o_lo)
+                ep.out_f32_nchw = L.ptr(y)
+                ep.slope, ep.act_scale, ep.activate = 0.2, SQRT2, 1
+                if not sp.up:
+                    ep.d = d.data_ptr()
+                    L.call("maua_modconv_tc", split[0].data_ptr(), split[1].data_ptr(), lp.w_hi.data_ptr(),
+                           lp.w_lo.data_ptr(), C.byref(ep), batch, sp.cin, sp.cout, in_h, in_w, 0, nprod, stream)
+                else:
+                    u = torch.empty((batch, 2 * in_h + 1, 2 * in_w + 1, sp.cout), device=device, dtype=torch.float32)
+                    ep_raw = L.ConvEpilogue()
+                    ep_raw.d, ep_raw.out_raw_nhwc, ep_raw.activate = d.data_ptr(), u.data_ptr(), 0
+                    L.call("maua_modconv_tc", split[0].data_ptr(), split[1].data_ptr(), lp.w_hi.data_ptr(),
+                           lp.w_lo.data_ptr(), C.byref(ep_raw), batch, sp.cin, sp.cout, in_h, in_w, 1, nprod, stream)
+                    L.call("maua_blur_act_nhwc", u.data_ptr(), conv.blur.kernel.data_ptr(), C.byref(ep), batch, sp.cout,
+                           2 * in_h + 1, 2 * in_w + 1, stream)
+                split = (o_hi, o_lo) if want_split else None
+                x, x_bstride = y, (y[0].numel() if y is not None else 0)
+            else:
+                # fp32 SIMT path, reference op order: conv -> [blur] -> noise -> bias+lrelu
+                if split is not None:
+                    raise L.MauaError("internal: split activations reached a SIMT layer")
+                xin = x.expand(batch, -1, -1, -1).contiguous() if x.shape[0] != batch else x
+                y = _modconv_simt(xin, conv.weight, s, d, conv.scale, 3, sp.up)
+                if sp.up:
+                    y = upfirdn2d(y, conv.blur.kernel, pad=conv.blur.pad)
+                y = _noise_bias_act(y, nz, sp.mod.noise.weight, sp.mod.activate.bias, 0.2, SQRT2)
+                x, x_bstride = y, y[0].numel()
+
+            if bend_here:
+                x = _bend(x, sp.layer_id, bends).contiguous()
+                x_bstride = x[0].numel()
+            if want_acts:
+                acts.append(x)
+            current_size *= 2 if (sp.up or li == 0) else 1
+            if sp.rgb is not None:
+                rs, _ = bc["views"][lp.rgb_job]
+                if g.min_rgb_size <= current_size:
+                    image = _torgb(x, sp.rgb.conv.weight, rs, sp.rgb.bias, image,
+                                   sp.rgb.upsample.kernel if image is not None else None, sp.rgb.conv.scale)
+
+        if want_u8 and image is not None:
+            image = frames_to_u8(image)
+    return image, latent_t, acts

@@ -1,0 +1,129 @@
+"""Network-level parity: our Generator (both conv implementations) vs the golden vectors produced by the unmodified
+reference, and vs the CPU oracle at BASELINE.json's config[0] shape (256x256, channel_multiplier=2).
+
+Metric (fixed once): max|a-b| / max|ref| per tensor, for the image and every activation map.
+Tolerance: 1e-3 (north_star); the fp32 SIMT path is held to 2e-5, the 3-product tensor-core path to 3e-4."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import stylegan2_oracle as O
+from tests.util import golden_inputs, make_generator, rel_err, strided
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"simt": 2e-5, "tc": 3e-4}
+
+
+def _run(g, gold, noise, **kw):
+    g.truncation_latent = torch.from_numpy(gold["truncation_latent"]).cuda()
+    with torch.no_grad():
+        return g(torch.from_numpy(gold["latent"]).cuda(), noise=[n.cuda() if n is not None else None for n in noise],
+                 truncation=torch.from_numpy(gold["psi"]).cuda(), input_is_latent=True, randomize_noise=False, **kw)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("fname", ["generator_g32.npz", "generator_g128.npz"])
+def test_generator_matches_reference_golden(fname, impl):
+    gold, noise = golden_inputs(fname)
+    g, sd = make_generator(int(gold["size"]), int(gold["cm"]), int(gold["seed"]), impl)
+    # mapping network (2-D path)
+    with torch.no_grad():
+        w = g.get_latent(torch.from_numpy(gold["z"]).cuda())
+    assert rel_err(w.cpu().numpy(), gold["w"]) < 1e-5
+    image, acts = _run(g, gold, noise, return_activation_maps=True)
+    errs = [rel_err(strided(a), gold[f"act_{l}"]) * float(np.abs(gold[f"act_{l}"]).max() / gold[f"act_{l}_absmax"])
+            for l, a in enumerate(acts)]
+    e_img = rel_err(image.cpu().numpy(), gold["image"])
+    print(f"{fname} {impl}: image {e_img:.2e} acts {['%.1e' % e for e in errs]}")
+    assert max(errs) < TOL[impl], errs
+    assert e_img < TOL[impl], e_img
+    # the fused path without activation maps must give the same image (different buffers / epilogue outputs)
+    image2, none = _run(g, gold, noise)
+    assert none is None
+    assert rel_err(image2.cpu().numpy(), image.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_generator_256_config0_vs_oracle(impl):
+    """BASELINE.json configs[0]: 256x256 random-init generator (cm=2); 3 of the 64 latents are checked against the
+    CPU oracle (≈1 s/frame), with a per-sample truncation and buffer noise for one layer."""
+    size, cm, seed, b = 256, 2, 0, 3
+    g, sd = make_generator(size, cm, seed, impl)
+    log_size, num_layers, n_latent = O.layout(size)
+    rng = np.random.Generator(np.random.PCG64(1))
+    z = torch.from_numpy(rng.standard_normal((b, 512)).astype(np.float32))
+    noise = [torch.from_numpy(rng.standard_normal((b, 1, 2 ** ((l + 5) // 2), 2 ** ((l + 5) // 2))).astype(np.float32))
+             for l in range(num_layers)]
+    noise[4] = None
+    psi = torch.from_numpy(rng.uniform(0.5, 1.0, b).astype(np.float32))
+    with torch.no_grad():
+        w = O.mapping(z, sd)
+        latent = w[:, None, :].repeat(1, n_latent, 1)
+        tl = w.mean(0, keepdim=True)
+        ref_img, ref_acts = O.generator_forward(sd, size, latent, noise, psi, tl, channel_multiplier=cm)
+        g.truncation_latent = tl.cuda()
+        img, acts = g(latent.cuda(), noise=[n.cuda() if n is not None else None for n in noise], truncation=psi.cuda(),
+                      input_is_latent=True, randomize_noise=False, return_activation_maps=True)
+    errs = [rel_err(a.cpu().numpy(), r.numpy()) for a, r in zip(acts, ref_acts)]
+    e_img = rel_err(img.cpu().numpy(), ref_img.numpy())
+    print(f"256 {impl}: image {e_img:.2e} acts {['%.1e' % e for e in errs]}")
+    assert max(errs) < TOL[impl] and e_img < TOL[impl]
+    # bytes: device-side uint8 NHWC pack vs render.py:40-43 semantics on our own fp32 image
+    from maua_stylegan2_b200.stylegan2 import frames_to_u8
+
+    u8 = frames_to_u8(img).cpu().numpy()
+    assert np.array_equal(u8, O.frames_to_u8(img.cpu()))
+    diff = np.abs(u8.astype(np.int32) - O.frames_to_u8(ref_img).astype(np.int32))
+    assert diff.max() <= 1  # truncation can flip a byte where the fp32 images differ by 1e-4
+
+
+def test_generator_api_surface():
+    g, sd = make_generator(32, 2, 3, "tc")
+    z = torch.randn(4, 512, device="cuda")
+    with torch.no_grad():
+        lat = g(z, map_latents=True)
+        assert lat.shape == (4, g.n_latent, 512)
+        g.truncation_latent = g.mean_latent(256)
+        img, lat_out = g([z], return_latents=True, truncation=0.7, randomize_noise=False)
+        assert img.shape == (4, 3, 32, 32) and lat_out.shape == (4, g.n_latent, 512)
+        # float truncation == tensor truncation
+        img2, _ = g(lat, input_is_latent=True, truncation=torch.full((4,), 0.7, device="cuda"), randomize_noise=False)
+        assert rel_err(img2.cpu().numpy(), img.cpu().numpy()) < 1e-6
+        # randomize_noise=True draws fresh noise: images differ, shape stays
+        img3, _ = g(lat, input_is_latent=True, truncation=0.7)
+        assert img3.shape == img.shape and not torch.equal(img3, img)
+        u8, _ = g(lat, input_is_latent=True, truncation=0.7, randomize_noise=False, return_u8=True)
+        assert u8.dtype == torch.uint8 and u8.shape == (4, 32, 32, 3)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_network_bend_changes_shape_like_reference(impl):
+    """A bend that doubles the width at layer 3 (tauceti/kelp-style padding): every later layer becomes non-square.
+    Checked against the oracle running the same torch transform."""
+    size, cm, seed, b = 32, 2, 3, 2
+    g, sd = make_generator(size, cm, seed, impl)
+
+    class Widen(torch.nn.Module):
+        def forward(self, x):
+            return torch.cat([x, torch.flip(x, [3])], 3)
+
+    bends = [{"layer": 3, "transform": Widen()}, {"layer": 0, "transform": torch.nn.Identity()}]
+    log_size, num_layers, n_latent = O.layout(size)
+    rng = np.random.Generator(np.random.PCG64(9))
+    latent = torch.from_numpy(rng.standard_normal((b, n_latent, 512)).astype(np.float32)) * 0.5
+    noise = []
+    for l in range(num_layers):
+        r = 2 ** ((l + 5) // 2)
+        wmul = 2 if l >= 3 else 1
+        noise.append(torch.from_numpy(rng.standard_normal((b, 1, r, r * wmul)).astype(np.float32)))
+    tl = torch.zeros(1, 512)
+    with torch.no_grad():
+        ref_img, ref_acts = O.generator_forward(sd, size, latent, noise, 1.0, tl, channel_multiplier=cm, bends=bends)
+        g.truncation_latent = tl.cuda()
+        img, acts = g(latent.cuda(), noise=[n.cuda() for n in noise], truncation=1.0, input_is_latent=True,
+                      transform_dict_list=bends, return_activation_maps=True)
+    assert img.shape == ref_img.shape == (b, 3, 32, 64)
+    assert rel_err(img.cpu().numpy(), ref_img.numpy()) < TOL[impl]
+    for a, r in zip(acts, ref_acts):
+        assert a.shape == r.shape and rel_err(a.cpu().numpy(), r.numpy()) < TOL[impl]

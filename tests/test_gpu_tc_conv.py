@@ -1,0 +1,152 @@
+"""Unit parity of the tensor-core modulated conv (maua_modconv_tc + blur_act_nhwc + layout kernels) against an
+fp64 CPU evaluation of the same formula.  Tolerance: 2e-4 of the tensor max for the
+3-product split-bf16 mode (north_star bar is 1e-3 on activations), 3e-2 for the single-product fast mode."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _pack(w, scale):
+    from maua_stylegan2_b200.plan import _pack_tc
+
+    return _pack_tc(w[None].contiguous(), scale)
+
+
+def _run_tc(x, w, s, d, noise, nw, bias, s_next, up, nprod, scale):
+    from maua_stylegan2_b200 import _lib as L
+    from maua_stylegan2_b200.synthesis import _modulate_split
+
+    b, cin, h, wd = x.shape
+    cout = w.shape[0]
+    w_hi, w_lo = _pack(w, scale)
+    hi, lo = _modulate_split(x, x[0].numel(), s, b)
+    stream = L.stream_ptr(x.device)
+    oh, ow = (2 * h, 2 * wd) if up else (h, wd)
+    y = torch.full((b, cout, oh, ow), float("nan"), device="cuda")
+    o_hi = torch.zeros((b, oh, ow, cout), device="cuda", dtype=torch.bfloat16)
+    o_lo = torch.zeros_like(o_hi)
+    ep = L.ConvEpilogue()
+    ep.noise, ep.noise_weight = noise.data_ptr(), nw.data_ptr()
+    ep.noise_bstride = oh * ow if noise.shape[0] == b else 0
+    ep.bias, ep.s_next = bias.data_ptr(), s_next.data_ptr()
+    ep.out_hi, ep.out_lo, ep.out_f32_nchw = o_hi.data_ptr(), o_lo.data_ptr(), y.data_ptr()
+    ep.slope, ep.act_scale, ep.activate = 0.2, 2 ** 0.5, 1
+    u = None
+    if not up:
+        ep.d = d.data_ptr()
+        L.call("maua_modconv_tc", hi.data_ptr(), lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), C.byref(ep), b, cin,
+               cout, h, wd, 0, nprod, stream)
+    else:
+        u = torch.full((b, 2 * h + 1, 2 * wd + 1, cout), float("nan"), device="cuda")
+        er = L.ConvEpilogue()
+        er.d, er.out_raw_nhwc, er.activate = d.data_ptr(), u.data_ptr(), 0
+        L.call("maua_modconv_tc", hi.data_ptr(), lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), C.byref(er), b, cin,
+               cout, h, wd, 1, nprod, stream)
+        k = torch.tensor([1.0, 3.0, 3.0, 1.0])
+        k4 = (k[None] * k[:, None] / 16).cuda()
+        L.call("maua_blur_act_nhwc", u.data_ptr(), k4.data_ptr(), C.byref(ep), b, cout, 2 * h + 1, 2 * wd + 1, stream)
+    torch.cuda.synchronize()
+    return y, o_hi, o_lo, u
+
+
+def _reference(x, w, s, d, noise, nw, bias, up, scale):
+    x, w, s, d, noise, nw, bias = (t.double().cpu() for t in (x, w, s, d, noise, nw, bias))
+    xs = x * s[:, :, None, None]
+    if not up:
+        o = F.conv2d(xs, w * scale, padding=1)
+        raw = None
+    else:
+        o = F.conv_transpose2d(xs, (w * scale).transpose(0, 1), stride=2)     # [B,Cout,2H+1,2W+1]
+        raw = (o * d[:, :, None, None]).permute(0, 2, 3, 1)
+        k = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=torch.float64)
+        k4 = (k[None] * k[:, None] / 16)
+        c = o.shape[1]
+        o = F.conv2d(F.pad(o, [1, 1, 1, 1]), torch.flip(k4, [0, 1])[None, None].repeat(c, 1, 1, 1), groups=c)
+    o = o * d[:, :, None, None]
+    o = o + nw * noise + bias[None, :, None, None]
+    return F.leaky_relu(o, 0.2) * 2 ** 0.5, raw
+
+
+CASES = [
+    # b, cin, cout, h, w, up
+    (2, 64, 64, 16, 16, False),
+    (3, 32, 32, 20, 12, False),      # KC=32 path, non power-of-two image
+    (8, 512, 512, 4, 4, False),      # batch folded into the M tile
+    (2, 128, 256, 32, 32, False),    # BN=256
+    (1, 64, 32, 40, 24, False),
+    (2, 64, 64, 8, 8, True),
+    (3, 128, 64, 16, 12, True),
+    (8, 512, 512, 4, 4, True),
+    (1, 64, 32, 32, 32, True),       # KC=64, BN=32, 4 phases
+    (2, 32, 16, 9, 7, True),         # odd sizes
+]
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w,up", CASES)
+def test_tc_conv_matches_fp64_reference(b, cin, cout, h, w, up):
+    torch.manual_seed(b * 1000 + cin + cout + h)
+    x = torch.randn(b, cin, h, w, device="cuda")
+    wt = torch.randn(cout, cin, 3, 3, device="cuda")
+    s = 1 + 0.5 * torch.randn(b, cin, device="cuda")
+    d = 0.5 + torch.rand(b, cout, device="cuda")
+    oh, ow = (2 * h, 2 * w) if up else (h, w)
+    noise = torch.randn(b, 1, oh, ow, device="cuda")
+    nw = torch.tensor([0.3], device="cuda")
+    bias = 0.1 * torch.randn(cout, device="cuda")
+    s_next = 1 + 0.5 * torch.randn(b, cout, device="cuda")
+    scale = 1 / (cin * 9) ** 0.5
+    ref, raw = _reference(x, wt, s, d, noise, nw, bias, up, scale)
+    y, o_hi, o_lo, u = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 3, scale)
+    if up:
+        assert rel_err(u.cpu().numpy(), raw.numpy()) < 2e-4, "raw transposed-conv phases"
+    assert not torch.isnan(y).any()
+    e = rel_err(y.cpu().numpy(), ref.numpy())
+    assert e < 2e-4, f"fp32 NCHW output rel err {e}"
+    rec = (o_hi.float() + o_lo.float()).permute(0, 3, 1, 2).cpu().double() / s_next.cpu().double()[:, :, None, None]
+    e2 = rel_err(rec.numpy(), ref.numpy())
+    assert e2 < 3e-4, f"split NHWC output rel err {e2}"
+
+
+def test_tc_conv_single_product_mode_is_bf16_grade():
+    torch.manual_seed(5)
+    b, cin, cout, h, w = 2, 64, 64, 16, 16
+    x = torch.randn(b, cin, h, w, device="cuda")
+    wt = torch.randn(cout, cin, 3, 3, device="cuda")
+    s = torch.ones(b, cin, device="cuda")
+    d = torch.ones(b, cout, device="cuda")
+    noise = torch.zeros(1, 1, h, w, device="cuda")
+    nw = torch.zeros(1, device="cuda")
+    bias = torch.zeros(cout, device="cuda")
+    scale = 1 / (cin * 9) ** 0.5
+    ref, _ = _reference(x, wt, s, d, noise, nw, bias, False, scale)
+    y, *_ = _run_tc(x, wt, s, d, noise, nw, bias, torch.ones(b, cout, device="cuda"), False, 1, scale)
+    e = rel_err(y.cpu().numpy(), ref.numpy())
+    assert 1e-5 < e < 3e-2, e
+
+
+def test_layout_kernels():
+    from maua_stylegan2_b200.synthesis import _modulate_split
+
+    torch.manual_seed(6)
+    x = torch.randn(3, 40, 5, 7, device="cuda")
+    s = torch.randn(3, 40, device="cuda")
+    hi, lo = _modulate_split(x, x[0].numel(), s, 3)
+    want = (x * s[:, :, None, None]).permute(0, 2, 3, 1)
+    assert torch.equal(hi, want.to(torch.bfloat16))
+    assert (hi.float() + lo.float() - want).abs().max() <= want.abs().max() * 2 ** -16
+    # broadcast (constant input) form
+    hi1, lo1 = _modulate_split(x[:1], 0, s, 3)
+    want1 = (x[:1] * s[:, :, None, None]).permute(0, 2, 3, 1)
+    assert torch.equal(hi1, want1.to(torch.bfloat16))
+    w = torch.randn(1, 24, 40, 3, 3, device="cuda")
+    w_hi, w_lo = _pack(w[0], 0.25)
+    wantw = (w[0] * 0.25).permute(2, 3, 0, 1).reshape(9, 24, 40)
+    assert torch.equal(w_hi, wantw.to(torch.bfloat16))
+    assert (w_hi.float() + w_lo.float() - wantw).abs().max() <= wantw.abs().max() * 2 ** -16
