@@ -99,7 +99,8 @@ def test_generator_api_surface():
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 def test_network_bend_changes_shape_like_reference(impl):
-    """A bend that doubles the width at layer 3 (tauceti/kelp-style padding): every later layer becomes non-square.
+    """A bend that doubles the width at layer 1, before the first ToRGB (kelp-style padding): every later layer
+    and the RGB skip become non-square.
     Checked against the oracle running the same torch transform."""
     size, cm, seed, b = 32, 2, 3, 2
     g, sd = make_generator(size, cm, seed, impl)
@@ -108,14 +109,14 @@ def test_network_bend_changes_shape_like_reference(impl):
         def forward(self, x):
             return torch.cat([x, torch.flip(x, [3])], 3)
 
-    bends = [{"layer": 3, "transform": Widen()}, {"layer": 0, "transform": torch.nn.Identity()}]
+    bends = [{"layer": 1, "transform": Widen()}, {"layer": 0, "transform": torch.nn.Identity()}]
     log_size, num_layers, n_latent = O.layout(size)
     rng = np.random.Generator(np.random.PCG64(9))
     latent = torch.from_numpy(rng.standard_normal((b, n_latent, 512)).astype(np.float32)) * 0.5
     noise = []
     for l in range(num_layers):
         r = 2 ** ((l + 5) // 2)
-        wmul = 2 if l >= 3 else 1
+        wmul = 2 if l >= 1 else 1
         noise.append(torch.from_numpy(rng.standard_normal((b, 1, r, r * wmul)).astype(np.float32)))
     tl = torch.zeros(1, 512)
     with torch.no_grad():
