@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the StyleGAN2 synthesis hot path at BASELINE.json configs[1]
+(1024x1024 config-f generator, 30 s of audio @30 fps = 900 frames, default-hook shaped latents/noise, batch 8).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, NCCL)
+
+A step = one pass of the hot path over one batch of `--batch` frames (per GPU; weak scaling): style prologue, 17
+modulated convs (tcgen05 path, 3-product split-bf16 = parity grade), blur/noise/bias/lrelu epilogues, 9 ToRGB, uint8
+NHWC pack, and for N > 1 one NCCL all-gather of the uint8 frames.
+  value    : frames/s with latents/noise resident in HBM, CUDA events around exactly K steps, max over ranks.
+  e2e      : frames/s through the public frame loop (maua_stylegan2_b200.render.FramePipeline): pinned host
+             latents/noise -> H2D every step, synthesis, uint8 frames -> D2H into pinned memory, inside the timed region.
+  roofline : dominant kernel = maua_modconv_tc (tensor-bound); achieved = algorithmic conv FLOPs / summed kernel time
+             measured live with CUDA events around every launch of K extra instrumented steps.
+  cpu_baseline / --impl reference : the oracle port of the reference's CPU path (oracle/stylegan2_oracle.py,
+             torch CPU fp32, all host threads) on a bounded sample of the same workload.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZE, CM, FPS, AUDIO_S = 1024, 2, 30, 30
+CONV_GFLOP_PER_FRAME = 148.52  # BASELINE.md §3 (2*MAC, algorithmic)
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    f = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(f):
+        try:
+            m = json.load(open(f))
+            p.update({k: float(m[k]) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+            p["source"] = "measured"
+        except Exception:
+            pass
+    return p
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workload (synthetic, shape-faithful to audioreactive/examples/default.py)
+# ----------------------------------------------------------------------------------------------------------------
+
+def make_workload(n_frames, seed=0):
+    """Host tensors: latents [n_frames,18,512] (smooth mixture of 12 'selected' W+ rows, like chroma-weighted latents),
+    noise: per-frame maps for widths <= 256 (examples/default.py:29-30 returns None above -> buffer noise)."""
+    import numpy as np
+    import torch
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sel = torch.from_numpy(rng.standard_normal((12, 18, 512)).astype(np.float32))
+    wgt = torch.from_numpy(rng.uniform(0, 1, (n_frames, 12)).astype(np.float32))
+    k = torch.hann_window(31, periodic=False)
+    k = (k / k.sum())[None, None]
+    wgt = torch.nn.functional.conv1d(torch.nn.functional.pad(wgt.t()[:, None], (15, 15), mode="circular"), k)[:, 0].t()
+    wgt = wgt / wgt.sum(1, keepdim=True)
+    latents = torch.einsum("tn,nld->tld", wgt, sel).contiguous()
+    noise = []
+    num_layers = (10 - 2) * 2 + 1
+    g = torch.Generator().manual_seed(seed)
+    for l in range(num_layers):
+        r = 2 ** ((l + 5) // 2)
+        noise.append(torch.randn(n_frames, 1, r, r, generator=g) if r <= 256 else None)
+    return latents, noise
+
+
+def make_generator(device, impl="tc", precision="bf16x3", seed=0):
+    import torch
+
+    from maua_stylegan2_b200.stylegan2 import Generator
+
+    torch.manual_seed(seed)
+    g = Generator(SIZE, 512, 8, channel_multiplier=CM, constant_input=True, output_size=SIZE, impl=impl,
+                  precision=precision)
+    with torch.no_grad():  # zero-initialised parameters get N(0, 0.1^2) so noise/bias paths do real work
+        for name, prm in g.named_parameters():
+            if name.endswith("noise.weight") or name.endswith("activate.bias") or (name.startswith("to_rgb") and name.endswith(".bias")):
+                prm.normal_(0, 0.1)
+    g = g.to(device).eval()
+    g.truncation_latent = torch.zeros(1, 512, device=device)
+    return g
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                       "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+            out["sm_mhz"] = statistics.median(busy)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ----------------------------------------------------------------------------------------------------------------
+
+def cpu_port_run(steps, warmup, budget_s=150.0, frames_per_step=1):
+    import numpy as np
+    import torch
+
+    from oracle import stylegan2_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    sd = O.synth_state_dict(SIZE, channel_multiplier=CM, seed=0)
+    _, num_layers, n_latent = O.layout(SIZE)
+    rng = np.random.Generator(np.random.PCG64(1))
+    latent = torch.from_numpy(rng.standard_normal((frames_per_step, n_latent, 512)).astype(np.float32)) * 0.5
+    noise = [torch.from_numpy(rng.standard_normal((frames_per_step, 1, 2 ** ((l + 5) // 2), 2 ** ((l + 5) // 2))).astype(np.float32))
+             if 2 ** ((l + 5) // 2) <= 256 else None for l in range(num_layers)]
+    tl = torch.zeros(1, 512)
+
+    def one():
+        with torch.no_grad():
+            img, _ = O.generator_forward(sd, SIZE, latent, noise, 1.0, tl, channel_multiplier=CM)
+            O.frames_to_u8(img)
+
+    t_w = time.perf_counter()
+    for _ in range(max(1, warmup)):
+        one()
+        if time.perf_counter() - t_w > budget_s / 3:
+            break
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        one()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"fps": done * frames_per_step / dt, "cores": cores, "steps_done": done, "seconds": dt,
+            "sample": f"{done} step(s) x {frames_per_step} frame of the 1024x1024 config-f batch (oracle port, torch CPU fp32, "
+                      f"{cores} threads)"}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--conv", default="tc", choices=["tc", "simt"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": "configs[1]: 1024x1024 config-f generator (channel_multiplier=2), 30 s audio @30 fps = 900 "
+                          "frames, default-hook shaped latents [900,18,512] + per-frame noise for widths <= 256",
+              "batch_per_gpu": args.batch, "global_batch": args.batch * world, "parallelism": f"frames sharded dp{world}",
+              "l2": "per-step working set (activations ~2.4 GB at batch 8) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_port_run(args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "1024x1024 frames/sec", "value": r["fps"], "unit": "frames/s",
+                "n_gpus": args.gpus, "steps": r["steps_done"], "warmup": args.warmup,
+                "ms_per_step": 1000.0 * r["seconds"] / max(r["steps_done"], 1), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"], "cpu": cpu_model()},
+                "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from maua_stylegan2_b200 import _lib as L
+    from maua_stylegan2_b200.parallel import AllGatherFrames, init_from_env
+    from maua_stylegan2_b200.render import FramePipeline
+
+    rank, world, local_rank = init_from_env()
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    pk = peaks()
+    B = args.batch
+    n_frames = FPS * AUDIO_S
+    latents_h, noise_h = make_workload(n_frames)
+    g = make_generator(device, impl=args.conv, precision=args.precision)
+    latents_d = latents_h.to(device)
+    noise_d = [n.to(device) if n is not None else None for n in noise_h]
+    nb = n_frames // B
+    gather = AllGatherFrames(world) if world > 1 else None
+
+    def step(i):
+        # rank-strided batches; inputs are already resident in HBM
+        n = ((i * world + rank) % nb) * B
+        frames, _ = g(latents_d[n:n + B], noise=[x[n:n + B] if x is not None else None for x in noise_d],
+                      truncation=1.0, input_is_latent=True, randomize_noise=False, return_u8=True)
+        if gather is not None:
+            work, out = gather(frames, i & 1)
+            work.wait()
+            return out
+        return frames
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            step(i)
+        torch.cuda.synchronize()
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        l0 = L.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        launches = L.launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        lt = torch.tensor([float(launches)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        ms_total = float(ms.item())
+        value = args.steps * B * world / (ms_total / 1000.0)
+
+        # ---- e2e through the public frame loop (host buffers, H2D + D2H inside the timed region) -----------------
+        def e2e_run(n_steps, offset):
+            lo = offset * B * world
+            hi = lo + n_steps * B * world
+            idx = [j % n_frames for j in range(lo, hi)]
+            pipe = FramePipeline(g, latents_h[idx], [x[idx] if x is not None else None for x in noise_h], B,
+                                 truncation=1.0, rank=rank, world=world)
+            sink_bytes = [0]
+
+            def consume(frames):
+                sink_bytes[0] += int(frames[:, ::64, ::64].sum()) * 0 + frames.nbytes  # touch the host frames
+
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            pipe.run(consume if rank == 0 else None, gather)
+            torch.cuda.synchronize()
+            barrier()
+            return time.perf_counter() - t0, pipe
+
+        e2e_run(args.warmup, 0)
+        dt, pipe = e2e_run(args.steps, args.warmup)
+        dtt = torch.tensor([dt], device=device)
+        if world > 1:
+            dist.all_reduce(dtt, op=dist.ReduceOp.MAX)
+        e2e = {"value": args.steps * B * world / float(dtt.item()), "unit": "frames/s",
+               "h2d_bytes_per_step": pipe.h2d_bytes // args.steps, "d2h_bytes_per_step": pipe.d2h_bytes // max(args.steps, 1),
+               "api": "maua_stylegan2_b200.render.FramePipeline (pinned host latents/noise -> uint8 frames in pinned host memory)"}
+
+        # ---- roofline pass: CUDA events around every launch of the hot kernels (rank 0, a few extra steps) --------
+        roof = roof_ufd = shares = None
+        if rank == 0:
+            names = {"maua_modconv_tc", "maua_modconv_simt_f32", "maua_blur_act_nhwc", "maua_torgb_f32",
+                     "maua_modulate_split_nhwc", "maua_style_prologue_f32", "maua_rgb_to_u8_nhwc", "maua_upfirdn2d_f32",
+                     "maua_noise_bias_act_f32"}
+            L.PROFILE = {"names": names, "events": []}
+            nprof = 3
+            for i in range(nprof):
+                step(1000 + i)
+            torch.cuda.synchronize()
+            ev = L.PROFILE["events"]
+            L.PROFILE = None
+            tot = {}
+            conv_ms, conv_fl = 0.0, 0.0
+            per_layer = {}
+            for name, tag, s, e in ev:
+                t = s.elapsed_time(e)
+                tot[name] = tot.get(name, 0.0) + t / nprof
+                if name in ("maua_modconv_tc", "maua_modconv_simt_f32") and tag is not None:
+                    conv_ms += t
+                    conv_fl += tag["flops"]
+                    key = f"L{tag['layer']}:{tag['cin']}->{tag['cout']}@{tag['h']}{'up' if tag['up'] else ''}"
+                    a = per_layer.setdefault(key, [0.0, 0.0])
+                    a[0] += t
+                    a[1] += tag["flops"]
+            shares = {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}
+            if conv_ms > 0:
+                ach = conv_fl / (conv_ms * 1e-3) / 1e12
+                nprod = 3 if (args.precision == "bf16x3" and args.conv == "tc") else 1
+                roof = {"kernel": "maua_modconv_tc" if args.conv == "tc" else "maua_modconv_simt_f32", "bound": "tensor",
+                        "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " sustained bf16",
+                        "algorithmic_gflop_per_launch_set": conv_fl / nprof / 1e9,
+                        "products_per_mac": nprod, "issued_frac": nprod * ach / pk["bf16_tflops_sustained"],
+                        "ms_per_step": conv_ms / nprof,
+                        "per_layer_tflops": {k: round(v[1] / (v[0] * 1e-3) / 1e12, 2) for k, v in per_layer.items()}}
+            # standalone upfirdn2d (the public op) on the largest Blur of the frame: [B,32,2049,2049] -> [B,32,2048,2048]
+            from maua_stylegan2_b200 import op
+
+            bb = min(B, 4)
+            x = torch.randn(bb, 32, 2049, 2049, device=device)
+            kk = torch.tensor([1.0, 3.0, 3.0, 1.0], device=device)
+            k4 = kk[None] * kk[:, None] / 16
+            for _ in range(3):
+                y = op.upfirdn2d(x, k4, pad=(1, 1))
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            s.record()
+            for _ in range(reps):
+                y = op.upfirdn2d(x, k4, pad=(1, 1))
+            e.record()
+            torch.cuda.synchronize()
+            by = 4.0 * (x.numel() + y.numel())
+            gbs = by / (s.elapsed_time(e) / reps * 1e-3) / 1e9
+            roof_ufd = {"kernel": "maua_upfirdn2d_f32 (blur_tile)", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
+                        "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None,
+                        "shape": f"[{bb},32,2049,2049]->[{bb},32,2048,2048] fp32 (in+out {by / 1e9:.2f} GB > L2)"}
+            del x, y
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_port_run(steps=2, warmup=1, budget_s=40.0)
+        cpu = {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "cpu": cpu_model()}
+
+    if rank == 0:
+        line = {"metric": "1024x1024 frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16x3 (split-bf16 tensor-core products, fp32 accumulate; fp32-grade)" if args.precision == "bf16x3" and args.conv == "tc"
+                else ("bf16" if args.conv == "tc" else "f32"),
+                "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(lt.item()), "roofline": roof, "roofline_upfirdn2d": roof_ufd,
+                "kernel_ms_per_step": shares, "cpu_baseline": cpu,
+                "conv_gflop_per_frame": CONV_GFLOP_PER_FRAME}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

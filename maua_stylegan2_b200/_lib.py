@@ -92,5 +92,18 @@ def launch_count():
     return int(lib().maua_launch_count())
 
 
+# Optional per-launch timing (bench.py's roofline pass): PROFILE = {"names": set, "events": []}; TAG is attached to
+# every recorded launch by the caller (synthesis.py sets it to the layer's algorithmic work).
+PROFILE = None
+TAG = None
+
+
 def call(name, *args):
+    if PROFILE is not None and name in PROFILE["names"]:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        check(getattr(lib(), name)(*args), name)
+        end.record()
+        PROFILE["events"].append((name, TAG, start, end))
+        return
     check(getattr(lib(), name)(*args), name)

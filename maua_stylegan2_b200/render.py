@@ -1,0 +1,248 @@
+"""Frame loop — drop-in for the reference's `render.render` (render.py:14-192) on the B200 pipeline.
+
+Same call signature (generator, latents, noise, offset, duration, batch_size, out_size, output_file, audio_file,
+truncation, bends, rewrites, randomize_noise, ffmpeg_preset) plus two optional extensions: `sink` (any callable
+receiving a uint8 [n,H,W,3] numpy batch; default = an ffmpeg rawvideo pipe like the reference, render.py:58-91)
+and `world`/`rank` for frame sharding over GPUs.
+
+What changed underneath (SURVEY.md §2.1 "D2H + uint8 convert", §3.2):
+  * frames are clamped / scaled / packed to uint8 NHWC ON DEVICE (maua_rgb_to_u8_nhwc) — 3 B/pixel cross PCIe
+    instead of 12, and no per-image `.cpu().numpy().astype()` on the host;
+  * latents / noise / truncation / bend modulation are pinned once, each batch is copied H2D on a copy stream while
+    the previous batch is still rendering (double buffering), D2H lands in pinned ping-pong buffers;
+  * no 5-second `queue.get` timeouts: the writer is a plain bounded queue + thread that cannot silently truncate
+    the video when a batch is slow (render.py:37,97 hazard).
+"""
+import queue
+import subprocess
+import threading
+
+import numpy as np
+import torch
+
+from .stylegan2 import frames_to_u8
+
+
+def _pin(t):
+    if t is None:
+        return None
+    t = t.float().contiguous()
+    return t.pin_memory() if not t.is_cuda else t
+
+
+class FramePipeline:
+    """Batches -> generator -> uint8 NHWC frames in pinned host memory, double-buffered over two CUDA streams."""
+
+    def __init__(self, generator, latents, noise, batch_size, truncation=1.0, bends=None, rewrites=None,
+                 randomize_noise=False, device=None, rank=0, world=1):
+        self.g = generator
+        self.device = device or next(generator.parameters()).device
+        self.batch = batch_size
+        self.rank, self.world = rank, world
+        self.latents = _pin(latents)
+        self.noise = [_pin(n) for n in noise]
+        self.truncation = truncation if isinstance(truncation, float) else _pin(truncation)
+        self.bends = bends or []
+        for bend in self.bends:
+            if "modulation" in bend:
+                bend["modulation"] = _pin(bend["modulation"])
+        self.rewrites = rewrites or {}
+        self.randomize_noise = randomize_noise
+        self.n_frames = len(self.latents)
+        self.starts = list(range(0, self.n_frames, batch_size))
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._host = [None, None]
+
+    # -- one batch -------------------------------------------------------------------------------------------------
+    def _stage(self, n):
+        """H2D of batch n on the copy stream (pinned -> device, non_blocking); returns a dict of device tensors."""
+        sl = slice(n, n + self.batch)
+        with torch.cuda.stream(self.copy_stream):
+            item = {"latent": self.latents[sl].to(self.device, non_blocking=True)}
+            self.h2d_bytes += item["latent"].numel() * 4
+            item["noise"] = []
+            for ns in self.noise:
+                if ns is None:
+                    item["noise"].append(None)
+                elif ns.shape[0] == 1:
+                    item["noise"].append(ns.to(self.device, non_blocking=True))
+                else:
+                    t = ns[sl].to(self.device, non_blocking=True)
+                    self.h2d_bytes += 0 if ns.is_cuda else t.numel() * 4
+                    item["noise"].append(t)
+            if isinstance(self.truncation, float):
+                item["truncation"] = self.truncation
+            else:
+                item["truncation"] = self.truncation[sl].to(self.device, non_blocking=True)
+                self.h2d_bytes += item["truncation"].numel() * 4
+            item["bends"] = []
+            for bend in self.bends:
+                if "modulation" in bend:
+                    mod = bend["modulation"][sl].to(self.device, non_blocking=True)
+                    self.h2d_bytes += mod.numel() * 4
+                    item["bends"].append({"layer": bend["layer"], "transform": bend["transform"](mod)})
+                else:
+                    item["bends"].append({"layer": bend["layer"], "transform": bend["transform"]})
+            item["ready"] = torch.cuda.Event()
+            item["ready"].record(self.copy_stream)
+        return item
+
+    def _apply_rewrites(self, n):
+        # render.py:160-167 (with the Tensor.copy() bug fixed: originals are cloned once)
+        if not self.rewrites:
+            return
+        if not hasattr(self, "_orig"):
+            params = dict(self.g.named_parameters())
+            self._orig = {k: params[k].detach().clone() for k in self.rewrites}
+        for name, (rewrite, modulation) in self.rewrites.items():
+            transform = rewrite(modulation[n:n + self.batch])
+            new = transform(self._orig[name]).to(self.device)
+            mod = self.g
+            parts = name.split(".")
+            for a in parts[:-1]:
+                mod = getattr(mod, a)
+            setattr(mod, parts[-1], torch.nn.Parameter(new, requires_grad=False))
+
+    def _render(self, item, n):
+        torch.cuda.current_stream(self.device).wait_event(item["ready"])
+        self._apply_rewrites(n)
+        frames, _ = self.g(styles=item["latent"], noise=item["noise"], truncation=item["truncation"],
+                           transform_dict_list=item["bends"], randomize_noise=self.randomize_noise,
+                           input_is_latent=True, return_u8=True)
+        return frames  # uint8 [b,H,W,3] on device
+
+    def run(self, consume, gather=None):
+        """Render every frame; `consume(np.uint8 [n,H,W,3])` is called in frame order on ranks where it is not None.
+
+        world == 1: step i renders batch i.   world > 1: step i renders batches i*world + rank (rank-strided, so one
+        all-gather yields world*B CONSECUTIVE frames); `gather(frames_u8) -> (work, out_u8)` is the
+        collective hook (see parallel.AllGatherFrames).  Short tails are padded by repeating the last frame and
+        trimmed before `consume`.  H2D of step i+1 (copy stream) and D2H of step i-1 (d2h stream) overlap the
+        synthesis of step i (compute stream)."""
+        world, rank = (self.world, self.rank) if gather is not None else (1, 0)
+        nb = len(self.starts)
+        steps = (nb + world - 1) // world
+        cur = torch.cuda.current_stream(self.device)
+        d2h = torch.cuda.Stream(self.device)
+
+        def batch_start(step):
+            return self.starts[min(step * world + rank, nb - 1)]
+
+        def finish(p):
+            p["done"].synchronize()
+            if consume is not None:
+                consume(p["host"].numpy()[:p["valid"]])
+
+        pending = None
+        nxt = self._stage(batch_start(0)) if steps else None
+        for i in range(steps):
+            item = nxt
+            nxt = self._stage(batch_start(i + 1)) if i + 1 < steps else None
+            n = batch_start(i)
+            frames = self._render(item, n)
+            if frames.shape[0] < self.batch:  # short tail: pad by repeating the last frame (equal-size collective)
+                frames = torch.cat([frames, frames[-1:].expand(self.batch - frames.shape[0], -1, -1, -1)], 0)
+            valid = min(self.n_frames - i * world * self.batch, world * self.batch)
+            work = None
+            if gather is not None:
+                work, out = gather(frames, i & 1)   # async collective on NCCL's stream; compute does not wait for it
+            else:
+                out = frames
+            if consume is not None:
+                slot = i & 1
+                if self._host[slot] is None or self._host[slot].shape != out.shape:
+                    self._host[slot] = torch.empty(out.shape, dtype=torch.uint8).pin_memory()
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                with torch.cuda.stream(d2h):
+                    if work is not None:
+                        work.wait()                 # the d2h stream (not the compute stream) waits for the gather
+                    d2h.wait_event(ready)
+                    self._host[slot].copy_(out, non_blocking=True)
+                    out.record_stream(d2h)
+                    done = torch.cuda.Event()
+                    done.record(d2h)
+                self.d2h_bytes += out.numel()
+                if pending is not None:
+                    finish(pending)                 # frames of step i-1 (other ping-pong slot)
+                pending = {"done": done, "host": self._host[slot], "valid": valid}
+        if pending is not None:
+            finish(pending)
+
+
+class FFmpegSink:
+    """rawvideo rgb24 on stdin -> libx264 yuv420p (+ 320k audio mux), the reference's wire format (render.py:58-91)."""
+
+    def __init__(self, output_file, width, height, fps, audio_file=None, offset=0, duration=None, preset="slow"):
+        cmd = ["ffmpeg", "-hide_banner", "-y", "-v", "warning", "-f", "rawvideo", "-pix_fmt", "rgb24", "-framerate",
+               str(fps), "-s", f"{width}x{height}", "-i", "pipe:"]
+        if audio_file is not None:
+            cmd += ["-ss", str(offset)] + (["-t", str(duration)] if duration else []) + ["-i", audio_file]
+        cmd += ["-framerate", str(fps), "-vcodec", "libx264", "-pix_fmt", "yuv420p", "-preset", preset]
+        if audio_file is not None:
+            cmd += ["-b:a", "320K", "-ac", "2"]
+        cmd += [output_file]
+        self.proc = subprocess.Popen(cmd, stdin=subprocess.PIPE)
+        self.q = queue.Queue(maxsize=8)
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def _loop(self):
+        while True:
+            frames = self.q.get()
+            if frames is None:
+                break
+            self.proc.stdin.write(frames.tobytes())
+        self.proc.stdin.close()
+        self.proc.wait()
+
+    def __call__(self, frames):
+        self.q.put(np.ascontiguousarray(frames).copy())
+
+    def close(self):
+        self.q.put(None)
+        self.t.join()
+
+
+def _fit_output(frames, out_size):
+    """render.py:98-105: 2048-wide/tall generators are cropped and resized to 1920x1080 / 1080x1920."""
+    import PIL.Image
+
+    out = []
+    for img in frames:
+        if img.shape[1] == 2048:
+            img = np.array(PIL.Image.fromarray(img[:, 112:-112, :]).resize((1920, 1080), PIL.Image.BILINEAR))
+        elif img.shape[0] == 2048:
+            img = np.array(PIL.Image.fromarray(img[112:-112, :, :]).resize((1080, 1920), PIL.Image.BILINEAR))
+        out.append(img)
+    return np.stack(out)
+
+
+def render(generator, latents, noise, offset, duration, batch_size, out_size, output_file, audio_file=None,
+           truncation=1.0, bends=[], rewrites={}, randomize_noise=False, ffmpeg_preset="slow", sink=None):
+    sizes = {512: (512, 512), 1024: (1024, 1024), 1920: (1920, 1080), 1080: (1080, 1920)}
+    if out_size not in sizes:
+        raise Exception("The only output sizes currently supported are: 512, 1024, 1080, or 1920")
+    w, h = sizes[out_size]
+    own_sink = sink is None
+    if own_sink:
+        sink = FFmpegSink(output_file, w, h, len(latents) / duration, audio_file, offset, duration, ffmpeg_preset)
+    if hasattr(generator, "module"):  # th.nn.DataParallel wrapper of the reference CLI (generate_audiovisual.py:54-55)
+        generator = generator.module
+    pipe = FramePipeline(generator, latents, list(noise), batch_size, truncation, bends, rewrites, randomize_noise)
+
+    def consume(frames):
+        if frames.shape[1] == 2048 or frames.shape[2] == 2048:
+            frames = _fit_output(frames, out_size)
+        assert frames.shape[2] == w and frames.shape[1] == h, (
+            f"generator's output image size does not match specified output size: \n"
+            f"got: {frames.shape[2]}x{frames.shape[1]}\t\tshould be {w}x{h}")
+        sink(frames)
+
+    with torch.no_grad():
+        pipe.run(consume)
+    if own_sink:
+        sink.close()
+    return pipe

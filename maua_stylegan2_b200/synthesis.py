@@ -92,6 +92,10 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
             if nz is None:  # randomize_noise=True: fresh N(0,1) per layer (models/stylegan2.py:263-265)
                 nz = torch.randn(batch, 1, out_h, out_w, device=device)
 
+            # algorithmic work of this layer: conv FLOPs = 2*H_in*W_in*Cin*Cout*9 per sample
+            L.TAG = {"layer": li, "up": sp.up, "cin": sp.cin, "cout": sp.cout, "h": in_h, "w": in_w,
+                     "flops": 2.0 * in_h * in_w * sp.cin * sp.cout * 9 * batch,
+                     "out_elems": float(batch) * sp.cout * out_h * out_w}
             if lp.tc_ok:
                 if split is None:
                     split = _modulate_split(x.contiguous(), x_bstride, s, batch)
