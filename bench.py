@@ -101,7 +101,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                       "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "50", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -147,7 +147,30 @@ def cpu_port_run(steps, warmup, budget_s=150.0, frames_per_step=1):
 
     from oracle import stylegan2_oracle as O
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if "MAUA_CPU_THREADS" in os.environ:
+        torch.set_num_threads(int(os.environ["MAUA_CPU_THREADS"]))
+    else:
+        # "all the host threads it can use": oneDNN grouped convs get SLOWER when oversubscribed (128 threads were 13x
+        # slower than 16 on the pool's hosts), so pick the fastest count on a quick 256x256 probe of the same code
+        sd_p = O.synth_state_dict(256, channel_multiplier=CM, seed=0)
+        _, nl_p, nlat_p = O.layout(256)
+        lat_p = torch.zeros(1, nlat_p, 512)
+        nz_p = [torch.zeros(1, 1, 2 ** ((l + 5) // 2), 2 ** ((l + 5) // 2)) for l in range(nl_p)]
+        best = (1e30, avail)
+        for t in sorted({min(avail, c) for c in (8, 16, 32, 64, avail)}):
+            torch.set_num_threads(t)
+            with torch.no_grad():
+                O.generator_forward(sd_p, 256, lat_p, nz_p, 1.0, torch.zeros(1, 512), channel_multiplier=CM)
+                t0 = time.perf_counter()
+                O.generator_forward(sd_p, 256, lat_p, nz_p, 1.0, torch.zeros(1, 512), channel_multiplier=CM)
+                dt = time.perf_counter() - t0
+            if dt < best[0]:
+                best = (dt, t)
+            if dt > 4 * best[0]:
+                break
+        torch.set_num_threads(best[1])
+        del sd_p
     cores = torch.get_num_threads()
     sd = O.synth_state_dict(SIZE, channel_multiplier=CM, seed=0)
     _, num_layers, n_latent = O.layout(SIZE)
@@ -262,11 +285,11 @@ def main():
             dist.barrier()
 
     with torch.no_grad():
+        sampler = ClockSampler(local_rank) if rank == 0 else None
         for i in range(args.warmup):
             step(i)
         torch.cuda.synchronize()
         barrier()
-        sampler = ClockSampler(local_rank) if rank == 0 else None
         l0 = L.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -292,6 +315,8 @@ def main():
             idx = [j % n_frames for j in range(lo, hi)]
             pipe = FramePipeline(g, latents_h[idx], [x[idx] if x is not None else None for x in noise_h], B,
                                  truncation=1.0, rank=rank, world=world)
+            if rank == 0:
+                pipe.prepare_host_buffers((SIZE, SIZE, 3))
             sink_bytes = [0]
 
             def consume(frames):
