@@ -269,11 +269,15 @@ def main():
     nb = n_frames // B
     gather = AllGatherFrames(world) if world > 1 else None
 
-    def step(i):
+    def step_local(i):
         # rank-strided batches; inputs are already resident in HBM
         n = ((i * world + rank) % nb) * B
         frames, _ = g(latents_d[n:n + B], noise=[x[n:n + B] if x is not None else None for x in noise_d],
                       truncation=1.0, input_is_latent=True, randomize_noise=False, return_u8=True)
+        return frames
+
+    def step(i):
+        frames = step_local(i)
         if gather is not None:
             work, out = gather(frames, i & 1)
             work.wait()
@@ -348,7 +352,7 @@ def main():
             L.PROFILE = {"names": names, "events": []}
             nprof = 3
             for i in range(nprof):
-                step(1000 + i)
+                step_local(1000 + i)   # no collective here: only rank 0 runs the instrumented pass
             torch.cuda.synchronize()
             ev = L.PROFILE["events"]
             L.PROFILE = None

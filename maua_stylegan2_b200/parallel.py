@@ -5,6 +5,7 @@ step and gathers fp32 images to GPU 0; here weights are replicated once and 3 B/
 
 The frame path has no other exchange step, so there is no other collective (frames are independent given their
 latents / noise / truncation rows)."""
+import datetime
 import os
 
 import torch
@@ -23,7 +24,8 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        # a mismatched collective must abort the job, not hang the box
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, timeout=datetime.timedelta(seconds=180))
     return rank, world, local_rank
 
 
