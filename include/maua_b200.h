@@ -173,6 +173,57 @@ int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w_hi, const 
 int maua_blur_act_nhwc(const float* u, const float* k4, const MauaConvEpilogue* ep_host, int batch, int ch, int hu,
                        int wu, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Audio feature chain (cuFFT-fronted; replaces the librosa/scipy CPU path of audioreactive/signal.py:31-156 and the
+ * latent glue of audioreactive/latent.py:15-26 + examples/default.py:12-25).  Spectrograms: [n_frames][n_bins]
+ * interleaved (re, im) fp32, n_bins = n_fft/2 + 1.  cuFFT plans (and their internal work areas) are cached inside the
+ * library per (size, batch, device); everything else is caller-allocated.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* librosa.stft(y, n_fft, hop, window=hann, center=True, pad_mode=reflect); frames_ws: n_frames*n_fft floats */
+int maua_audio_stft_f32(const float* y, long long n, float* spec, float* frames_ws, int n_fft, int hop, int n_frames,
+                        void* stream);
+/* librosa.istft(spec, hop, window=hann, center=True, length=n); `spec` may be clobbered */
+int maua_audio_istft_f32(float* spec, float* y, long long n, float* frames_ws, int n_fft, int hop, int n_frames,
+                         void* stream);
+/* librosa.decompose.hpss soft mask (median 31x1 / 1x31, `power`, `margin`) applied to spec; which: 0 harmonic, 1 percussive.
+ * mag_ws: n_frames*n_bins floats */
+int maua_audio_hpss_f32(const float* spec, float* spec_out, float* mag_ws, int n_frames, int n_bins, float margin,
+                        float power, int which, void* stream);
+/* out[t][m] = sum_f |spec[t][f]|^2 * fb[m][f]  (mel or chroma filterbank, fb dense [n_filters][n_bins]) */
+int maua_audio_filterbank_f32(const float* spec, const float* fb, float* out, int n_frames, int n_bins, int n_filters,
+                              void* stream);
+/* librosa.onset.onset_strength tail: mel (power, overwritten with dB) -> power_to_db(amin, top_db) -> lag-1 positive
+ * difference -> mean over bands -> left-pad `pad` frames.  scalar_ws: 1 float */
+int maua_audio_onset_env_f32(float* mel, float* env, float* scalar_ws, int n_frames, int n_mels, int pad, float amin,
+                             float top_db, void* stream);
+/* librosa.feature.rms(S=|spec|) */
+int maua_audio_rms_f32(const float* spec, float* rms, int n_frames, int n_bins, int n_fft, void* stream);
+/* CENS post-processing of a chromagram [n_frames][n_chroma]: L1, quantise, hann(win_len) smoothing, L2. ws: same size */
+int maua_audio_cens_f32(const float* raw, float* cens, float* ws, int n_frames, int n_chroma, int win_len, void* stream);
+/* np.minimum(x, nn_filter(x, aggregate=median, metric=cosine)) with k nearest frames; scratch: scratch_rows*n_frames floats */
+int maua_audio_nn_filter_f32(const float* x, float* out, float* scratch, int scratch_rows, int n_frames, int n_chroma,
+                             int k, void* stream);
+/* scipy.signal.resample along axis 0 of x[n_in][channels] (double precision inside).
+ * ws: (n_in + n_out)*C doubles + (n_in/2 + n_out/2 + 2)*C double2 */
+int maua_resample_f32(const float* x, float* y, double* ws, int n_in, int n_out, int channels, void* stream);
+/* x = clip(x, min(ref), max(ref))   (signal.py:68,94) */
+int maua_clip_to_range_f32(const float* ref, int n_ref, float* x, int n, void* stream);
+/* audioreactive.gaussian_filter (signal.py:319-368) along axis 0 of x[n_frames][inner], circular;
+ * causal_mode 0: symmetric, 1: future taps * causal, 2: future taps zeroed (non-float `causal`, e.g. 0) */
+int maua_gaussian_filter_f32(const float* x, float* y, int n_frames, long long inner, float sigma, float smf,
+                             int causal_mode, float causal, void* stream);
+/* audioreactive.percentile_clip (signal.py:273-292) followed by ** power */
+int maua_percentile_clip_f32(const float* x, float* y, int n, float percentile, float power, void* stream);
+/* scipy.signal.sosfilt (double-precision state), sos: [n_sections][6] doubles on the device */
+int maua_sosfilt_f32(const float* x, float* y, long long n, const double* sos, int n_sections, void* stream);
+/* latent.py:15-26: out[t][e] = sum_n chroma[t][n] * selection[n][e] */
+int maua_chroma_weight_latents_f32(const float* chroma, const float* selection, float* out, int n_frames, int n_select,
+                                   long long latent_elems, void* stream);
+/* examples/default.py:20-21: x[t][e] = envelope[t]*target[e] + (1 - envelope[t])*x[t][e] */
+int maua_envelope_blend_f32(float* x, const float* envelope, const float* target, int n_frames, long long inner,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

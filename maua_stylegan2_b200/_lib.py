@@ -45,6 +45,21 @@ SIGNATURES = {
     "maua_modulate_split_nhwc": [_p, _ll, _p, _p, _p, _i, _i, _i, _i, _p],
     "maua_modconv_tc": [_p, _p, _p, _p, C.POINTER(ConvEpilogue), _i, _i, _i, _i, _i, _i, _i, _p],
     "maua_blur_act_nhwc": [_p, _p, C.POINTER(ConvEpilogue), _i, _i, _i, _i, _p],
+    "maua_audio_stft_f32": [_p, _ll, _p, _p, _i, _i, _i, _p],
+    "maua_audio_istft_f32": [_p, _p, _ll, _p, _i, _i, _i, _p],
+    "maua_audio_hpss_f32": [_p, _p, _p, _i, _i, _f, _f, _i, _p],
+    "maua_audio_filterbank_f32": [_p, _p, _p, _i, _i, _i, _p],
+    "maua_audio_onset_env_f32": [_p, _p, _p, _i, _i, _i, _f, _f, _p],
+    "maua_audio_rms_f32": [_p, _p, _i, _i, _i, _p],
+    "maua_audio_cens_f32": [_p, _p, _p, _i, _i, _i, _p],
+    "maua_audio_nn_filter_f32": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "maua_resample_f32": [_p, _p, _p, _i, _i, _i, _p],
+    "maua_clip_to_range_f32": [_p, _i, _p, _i, _p],
+    "maua_gaussian_filter_f32": [_p, _p, _i, _ll, _f, _f, _i, _f, _p],
+    "maua_percentile_clip_f32": [_p, _p, _i, _f, _f, _p],
+    "maua_sosfilt_f32": [_p, _p, _ll, _p, _i, _p],
+    "maua_chroma_weight_latents_f32": [_p, _p, _p, _i, _i, _ll, _p],
+    "maua_envelope_blend_f32": [_p, _p, _p, _i, _ll, _p],
 }
 _SPECIAL = {
     "maua_abi_version": (C.c_int, []),

@@ -67,7 +67,7 @@ class FramePipeline:
         sl = slice(n, n + self.batch)
         with torch.cuda.stream(self.copy_stream):
             item = {"latent": self.latents[sl].to(self.device, non_blocking=True)}
-            self.h2d_bytes += item["latent"].numel() * 4
+            self.h2d_bytes += 0 if self.latents.is_cuda else item["latent"].numel() * 4
             item["noise"] = []
             for ns in self.noise:
                 if ns is None:
