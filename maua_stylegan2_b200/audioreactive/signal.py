@@ -119,7 +119,7 @@ def resample(x, num):
     flat = x.reshape(x.shape[0], -1)
     n_in, c = flat.shape
     y = th.empty((num, c), device=x.device, dtype=th.float32)
-    ws = th.empty((n_in + num) * c + 2 * (n_in // 2 + num // 2 + 2) * c, device=x.device, dtype=th.float64)
+    ws = th.empty((n_in + num) * c + 2 * (n_in // 2 + num // 2 + 2) * c + 2, device=x.device, dtype=th.float64)
     L.call("maua_resample_f32", flat.data_ptr(), y.data_ptr(), ws.data_ptr(), n_in, num, c, L.stream_ptr(x.device))
     return y.reshape((num,) + tuple(x.shape[1:]))
 

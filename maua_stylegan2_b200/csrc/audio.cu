@@ -674,8 +674,10 @@ extern "C" int maua_resample_f32(const float* x, float* y, double* ws, int n_in,
   MAUA_CHECK_ARG(x && y && ws && n_in >= 2 && n_out >= 2 && channels >= 1, "resample: bad arguments");
   cudaStream_t st = as_stream(stream);
   const long long C = channels;
+  MAUA_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "resample: workspace must be 16-byte aligned");
   double* xin = ws;
-  double2* X = reinterpret_cast<double2*>(xin + (long long)n_in * C);
+  const long long n_in_pad = ((long long)n_in * C + 1) & ~1LL;  // keep the complex buffers 16-byte aligned
+  double2* X = reinterpret_cast<double2*>(xin + n_in_pad);
   double2* Y = X + (long long)(n_in / 2 + 1) * C;
   double* yout = reinterpret_cast<double*>(Y + (long long)(n_out / 2 + 1) * C);
   f2d_kernel<<<nblocks((long long)n_in * C), 256, 0, st>>>(x, xin, (long long)n_in * C);

@@ -10,6 +10,8 @@
 // is staged in shared memory with 128-byte-contiguous loads; each thread slides down a column of 8 outputs for
 // one float4 of channels (44 LDS.128 per 8 outputs), stores are 8-byte bf16x4 per plane.
 #include "common.cuh"
+#include "sm100_ptx.cuh"
+#include "tmap.cuh"
 
 namespace maua {
 
@@ -115,6 +117,154 @@ __global__ void __launch_bounds__(256) blur_act_nhwc_kernel(const float* __restr
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA version (C % 32 == 0): persistent CTAs, the 19x19x32 fp32 input tile arrives by ONE cp.async.bulk.tensor per
+// tile (zero padding = TMA out-of-bounds fill, no bounds logic), double-buffered through two mbarriers so that the
+// load of tile i+2 overlaps the FMA/epilogue work of tile i+1.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_tile_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3) {
+  ptx::tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+}
+
+__global__ void __launch_bounds__(256, 2) blur_act_nhwc_tma_kernel(const __grid_constant__ CUtensorMap tm_u,
+                                                                   const float* __restrict__ k4, MauaConvEpilogue ep,
+                                                                   int batch, int ch, int hu, int wu, int n_tiles) {
+  using namespace ptx;
+  constexpr uint32_t TILE_BYTES = BIN * BIN * BCH * 4;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const float* tile_ptr[2];
+  {
+    const uintptr_t g = (reinterpret_cast<uintptr_t>(smem_raw) + 127u) & ~static_cast<uintptr_t>(127u);
+    tile_ptr[0] = reinterpret_cast<const float*>(g);
+    tile_ptr[1] = reinterpret_cast<const float*>(g + TILE_BYTES);
+  }
+  const uint32_t bar0 = base + 2 * TILE_BYTES;
+  __shared__ float kf[16];
+  const int tid = threadIdx.x;
+  const int oh = hu - 1, ow = wu - 1;
+  const int tiles_x = (ow + BT - 1) / BT, tiles_y = (oh + BT - 1) / BT, ncg = ch / BCH;
+
+  if (tid < 16) kf[tid] = __ldg(k4 + (3 - (tid >> 2)) * 4 + (3 - (tid & 3)));  // flipped
+  if (tid == 0) {
+    prefetch_tmap(&tm_u);
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto decode = [&](int t, int& cg, int& ox0, int& oy0, int& b) {
+    cg = t % ncg;
+    int r = t / ncg;
+    ox0 = (r % tiles_x) * BT;
+    r /= tiles_x;
+    oy0 = (r % tiles_y) * BT;
+    b = r / tiles_y;
+  };
+  auto issue = [&](int t, int stage) {
+    int cg, ox0, oy0, b;
+    decode(t, cg, ox0, oy0, b);
+    mbar_expect_tx(bar0 + 8 * stage, TILE_BYTES);
+    tma_load_tile_4d(base + stage * TILE_BYTES, &tm_u, bar0 + 8 * stage, cg * BCH, ox0 - 1, oy0 - 1, b);
+  };
+
+  const int first = blockIdx.x, step = gridDim.x;
+  if (tid == 0) {
+    if (first < n_tiles) issue(first, 0);
+    if (first + step < n_tiles) issue(first + step, 1);
+  }
+  float kk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kk[i] = kf[i];
+  const int c4 = tid & 7;
+  const int p = tid >> 3;
+  const int lx = p & 15;
+  const int ly0 = (p >> 4) * 8;
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(ep.out_hi);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(ep.out_lo);
+  const float nw = (ep.activate && ep.noise) ? __ldg(ep.noise_weight) : 0.f;
+
+  int it = 0;
+  for (int t = first; t < n_tiles; t += step, ++it) {
+    const int stage = it & 1;
+    mbar_wait(bar0 + 8 * stage, (it >> 1) & 1);
+    const float* tile = tile_ptr[stage];
+    float4 acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 11; ++r) {
+      float4 row[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        row[e] = *reinterpret_cast<const float4*>(&tile[((ly0 + r) * BIN + lx + e) * BCH + c4 * 4]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int a = r - j;
+        if (a >= 0 && a < 4) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float kv = kk[a * 4 + e];
+            acc[j].x = fmaf(row[e].x, kv, acc[j].x);
+            acc[j].y = fmaf(row[e].y, kv, acc[j].y);
+            acc[j].z = fmaf(row[e].z, kv, acc[j].z);
+            acc[j].w = fmaf(row[e].w, kv, acc[j].w);
+          }
+        }
+      }
+    }
+    __syncthreads();  // every thread has consumed this stage: refill it while the epilogue runs
+    if (tid == 0 && t + 2 * step < n_tiles) {
+      fence_proxy_async();
+      issue(t + 2 * step, stage);
+    }
+
+    int cg, ox0, oy0, b;
+    decode(t, cg, ox0, oy0, b);
+    const int cbase = cg * BCH + c4 * 4;
+    const int ox = ox0 + lx;
+    if (ox >= ow) continue;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), sn = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (ep.activate && ep.bias) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + cbase));
+    if (ep.s_next) sn = __ldg(reinterpret_cast<const float4*>(ep.s_next + (long long)b * ch + cbase));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int oy = oy0 + ly0 + j;
+      if (oy >= oh) break;
+      float v0 = acc[j].x, v1 = acc[j].y, v2 = acc[j].z, v3 = acc[j].w;
+      if (ep.activate) {
+        float nz = 0.f;
+        if (ep.noise) nz = __fmul_rn(nw, __ldg(ep.noise + (long long)b * ep.noise_bstride + (long long)oy * ow + ox));
+        v0 = lrelu_scaled(__fadd_rn(__fadd_rn(v0, nz), bias.x), ep.slope, ep.act_scale);
+        v1 = lrelu_scaled(__fadd_rn(__fadd_rn(v1, nz), bias.y), ep.slope, ep.act_scale);
+        v2 = lrelu_scaled(__fadd_rn(__fadd_rn(v2, nz), bias.z), ep.slope, ep.act_scale);
+        v3 = lrelu_scaled(__fadd_rn(__fadd_rn(v3, nz), bias.w), ep.slope, ep.act_scale);
+      }
+      if (ep.out_f32_nchw) {
+        float* o = ep.out_f32_nchw + (((long long)b * ch + cbase) * oh + oy) * ow + ox;
+        const long long plane = (long long)oh * ow;
+        o[0] = v0; o[plane] = v1; o[2 * plane] = v2; o[3 * plane] = v3;
+      }
+      if (hi) {
+        v0 *= sn.x; v1 *= sn.y; v2 *= sn.z; v3 *= sn.w;
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(v0 - f01.x, v1 - f01.y);
+        const __nv_bfloat162 l23 = __floats2bfloat162_rn(v2 - f23.x, v3 - f23.y);
+        const long long o = (((long long)b * oh + oy) * ow + ox) * ch + cbase;
+        uint2 ph, pl;
+        ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+        pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(hi + o) = ph;
+        *reinterpret_cast<uint2*>(lo + o) = pl;
+      }
+    }
+  }
+}
+
 }  // namespace maua
 
 extern "C" int maua_blur_act_nhwc(const float* u, const float* k4, const MauaConvEpilogue* ep_host, int batch, int ch,
@@ -127,6 +277,27 @@ extern "C" int maua_blur_act_nhwc(const float* u, const float* k4, const MauaCon
   if (batch == 0) return MAUA_OK;
   MAUA_CHECK_ARG(batch <= 65535, "blur_act_nhwc: batch too large");
   const int oh = hu - 1, ow = wu - 1;
+  if (ch % BCH == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0) {
+    CUtensorMap tm;
+    const cuuint64_t dims[4] = {(cuuint64_t)ch, (cuuint64_t)wu, (cuuint64_t)hu, (cuuint64_t)batch};
+    const cuuint64_t strides[3] = {(cuuint64_t)ch * 4, (cuuint64_t)wu * ch * 4, (cuuint64_t)hu * wu * ch * 4};
+    const cuuint32_t box[4] = {BCH, BIN, BIN, 1};
+    int rc = tmap::encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, u, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != MAUA_OK) return rc;
+    const long long n_tiles = (long long)ceil_div(ow, BT) * ceil_div(oh, BT) * (ch / BCH) * batch;
+    MAUA_CHECK_ARG(n_tiles < (1LL << 31), "blur_act_nhwc: too many tiles");
+    const size_t smem = 2 * (size_t)BIN * BIN * BCH * 4 + 16 + 128;
+    static bool attr_done = false;
+    if (!attr_done) {
+      MAUA_CHECK_CUDA(cudaFuncSetAttribute(blur_act_nhwc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+      attr_done = true;
+    }
+    const int grid = (int)(n_tiles < 148 * 2 ? n_tiles : 148 * 2);
+    blur_act_nhwc_tma_kernel<<<grid, 256, smem, as_stream(stream)>>>(tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles);
+    MAUA_CHECK_LAUNCH("blur_act_nhwc(tma)");
+    return MAUA_OK;
+  }
   dim3 grid(ceil_div(ow, BT) * ceil_div(oh, BT), ceil_div(ch, BCH), batch);
   blur_act_nhwc_kernel<<<grid, 256, 0, as_stream(stream)>>>(u, k4, *ep_host, ch, hu, wu);
   MAUA_CHECK_LAUNCH("blur_act_nhwc");

@@ -92,6 +92,58 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x,
   }
 }
 
+// Low-resolution variant (H*W <= 4096, Cin = 512): the serial channel loop of torgb_kernel is latency-bound there
+// (a handful of threads, 512 dependent iterations), so the channels are split over the 8 warps of the block
+// (32 pixels x 8 channel groups) and the partial sums are combined through shared memory.
+__global__ void __launch_bounds__(256) torgb_small_kernel(const float* __restrict__ x, const float* __restrict__ wrgb,
+                                                          const float* __restrict__ s, const float* __restrict__ bias,
+                                                          const float* __restrict__ skip, const float* __restrict__ k4,
+                                                          float* __restrict__ y, int cin, int h, int w, float w_scale) {
+  extern __shared__ float wr[];  // [3][cin]
+  __shared__ float kf[16];
+  __shared__ float part[3][8][32];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, cg = tid >> 5;
+  for (int i = tid; i < 3 * cin; i += 256) {
+    const int c = i % cin;
+    float v = __ldg(wrgb + i) * w_scale;
+    if (s) v *= __ldg(s + (long long)b * cin + c);
+    wr[i] = v;
+  }
+  if (tid < 16) kf[tid] = k4 ? __ldg(k4 + tid) : 0.f;
+  __syncthreads();
+  const int hw = h * w;
+  const int p = blockIdx.x * 32 + lane;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  if (p < hw) {
+    const float* xb = x + (long long)b * cin * hw + p;
+    // same accumulation order per partial (ascending c), partials combined in ascending group order below
+    for (int c = cg; c < cin; c += 8) {
+      const float xv = __ldg(xb + (long long)c * hw);
+      a0 = fmaf(xv, wr[c], a0);
+      a1 = fmaf(xv, wr[cin + c], a1);
+      a2 = fmaf(xv, wr[2 * cin + c], a2);
+    }
+  }
+  part[0][cg][lane] = a0;
+  part[1][cg][lane] = a1;
+  part[2][cg][lane] = a2;
+  __syncthreads();
+  if (cg < 3 && p < hw) {
+    const int r = cg;
+    float acc = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) acc += part[r][g][lane];
+    float o = __fadd_rn(acc, bias ? __ldg(bias + r) : 0.f);
+    if (skip) {
+      const int sh = h >> 1, sw = w >> 1;
+      const int oy = p / w, ox = p - oy * w;
+      o = __fadd_rn(o, skip_up2(skip + ((long long)b * 3 + r) * sh * sw, sh, sw, kf, oy, ox));
+    }
+    y[((long long)b * 3 + r) * hw + p] = o;
+  }
+}
+
 // one thread = one pixel (3 planar loads coalesced across the warp, 3 packed bytes out)
 __global__ void __launch_bounds__(256) rgb_to_u8_kernel(const float* __restrict__ rgb, uint8_t* __restrict__ out,
                                                         long long hw, long long total) {
@@ -124,7 +176,10 @@ extern "C" int maua_torgb_f32(const float* x, const float* wrgb, const float* s,
   const size_t smem = 3 * (size_t)cin * sizeof(float);
   const bool vec = (hw % 4 == 0) && (w % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
-  if (vec) {
+  if (hw <= 4096 && cin >= 64) {
+    dim3 grid((unsigned)ceil_div(hw, 32LL), batch);
+    torgb_small_kernel<<<grid, 256, smem, st>>>(x, wrgb, s, bias, skip, k4, y, cin, h, w, w_scale);
+  } else if (vec) {
     dim3 grid((unsigned)ceil_div(hw / 4, 256LL), batch);
     torgb_kernel<4><<<grid, 256, smem, st>>>(x, wrgb, s, bias, skip, k4, y, cin, h, w, w_scale);
   } else {

@@ -15,52 +15,95 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// grid (n_jobs, batch), 256 threads.  style_dim <= 1024, cin <= 1024.
-__global__ void __launch_bounds__(256) style_prologue_kernel(const MauaStyleJob* __restrict__ jobs,
-                                                             const float* __restrict__ latent,
-                                                             const float* __restrict__ mean,
-                                                             const float* __restrict__ psi, float psi_scalar,
-                                                             float* __restrict__ latent_trunc_out, int n_latent,
-                                                             int style_dim) {
-  __shared__ float sw[1024];
-  __shared__ float ss[1024];
+// Two launches per batch (all 26 modulated layers each):
+//   style_s_kernel: grid (n_jobs, ceil(max_cin/64), ceil(B/8)); block = 64 rows of one modulation matrix x 8 samples.
+//                   The truncated latents of the 8 samples sit in shared memory, every weight row is read once per
+//                   block and reused for the 8 samples (the first version re-read 1 MB of weights per (job, sample)).
+//   style_d_kernel: same tiling over Wsq rows for the demodulation vector (needs the complete s of the layer).
+constexpr int SB = 8;      // samples per block
+constexpr int SROWS = 64;  // weight rows per block (8 per warp)
+
+__global__ void __launch_bounds__(256) style_s_kernel(const MauaStyleJob* __restrict__ jobs,
+                                                      const float* __restrict__ latent, const float* __restrict__ mean,
+                                                      const float* __restrict__ psi, float psi_scalar,
+                                                      float* __restrict__ latent_trunc_out, int batch, int n_latent,
+                                                      int style_dim) {
+  extern __shared__ float sw[];  // [SB][style_dim]
   const MauaStyleJob job = jobs[blockIdx.x];
-  const int b = blockIdx.y;
+  const int row0 = blockIdx.y * SROWS;
+  if (row0 >= job.cin) return;
+  const int b0 = blockIdx.z * SB;
+  const int nb = min(SB, batch - b0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* lrow = latent + ((long long)b * n_latent + job.latent_index) * style_dim;
-  const float t = psi ? __ldg(psi + b) : psi_scalar;
-  for (int i = tid; i < style_dim; i += 256) {
-    float v = lrow[i];
+  for (int i = tid; i < nb * style_dim; i += 256) {
+    const int bl = i / style_dim, k = i - bl * style_dim;
+    const int b = b0 + bl;
+    float v = latent[((long long)b * n_latent + job.latent_index) * style_dim + k];
     if (mean) {
-      const float m = __ldg(mean + i);
+      const float m = __ldg(mean + k);
+      const float t = psi ? __ldg(psi + b) : psi_scalar;
       v = __fadd_rn(m, __fmul_rn(t, __fsub_rn(v, m)));  // w_bar + psi * (w - w_bar), models/stylegan2.py:541-543
     }
     sw[i] = v;
-    if (latent_trunc_out) latent_trunc_out[((long long)b * n_latent + job.latent_index) * style_dim + i] = v;
+    if (latent_trunc_out && blockIdx.y == 0)
+      latent_trunc_out[((long long)b * n_latent + job.latent_index) * style_dim + k] = v;
   }
   __syncthreads();
   const float lin_scale = rsqrtf((float)style_dim);
-  for (int ci = warp; ci < job.cin; ci += 8) {
-    const float* wr = job.mod_w + (long long)ci * style_dim;
-    float acc = 0.f;
-    for (int i = lane; i < style_dim; i += 32) acc = fmaf(sw[i], __ldg(wr + i), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float s = fmaf(acc, lin_scale, __ldg(job.mod_b + ci));
-      ss[ci] = s;
-      job.s_out[(long long)b * job.cin + ci] = s;
+  for (int r = row0 + warp; r < min(row0 + SROWS, job.cin); r += 8) {
+    const float* wr = job.mod_w + (long long)r * style_dim;
+    float acc[SB];
+#pragma unroll
+    for (int j = 0; j < SB; ++j) acc[j] = 0.f;
+    for (int k = lane; k < style_dim; k += 32) {
+      const float wv = __ldg(wr + k);
+#pragma unroll
+      for (int j = 0; j < SB; ++j) acc[j] = fmaf(sw[j * style_dim + k], wv, acc[j]);  // rows j >= nb read stale smem: unused
+    }
+#pragma unroll
+    for (int j = 0; j < SB; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane < nb) {
+      float a = acc[0];
+#pragma unroll
+      for (int j = 1; j < SB; ++j) a = (lane == j) ? acc[j] : a;
+      job.s_out[(long long)(b0 + lane) * job.cin + r] = fmaf(a, lin_scale, __ldg(job.mod_b + r));
     }
   }
-  if (job.wsq == nullptr) return;
+}
+
+__global__ void __launch_bounds__(256) style_d_kernel(const MauaStyleJob* __restrict__ jobs, int batch, int max_cin) {
+  extern __shared__ float ss[];  // [SB][cin] squared styles
+  const MauaStyleJob job = jobs[blockIdx.x];
+  const int row0 = blockIdx.y * SROWS;
+  if (job.wsq == nullptr || row0 >= job.cout) return;
+  const int b0 = blockIdx.z * SB;
+  const int nb = min(SB, batch - b0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < SB * job.cin; i += 256) {
+    const int bl = i / job.cin, k = i - bl * job.cin;
+    float v = 0.f;
+    if (bl < nb) v = job.s_out[(long long)(b0 + bl) * job.cin + k];
+    ss[i] = v * v;
+  }
   __syncthreads();
-  for (int i = tid; i < job.cin; i += 256) ss[i] = ss[i] * ss[i];
-  __syncthreads();
-  for (int co = warp; co < job.cout; co += 8) {
-    const float* wr = job.wsq + (long long)co * job.cin;
-    float acc = 0.f;
-    for (int i = lane; i < job.cin; i += 32) acc = fmaf(ss[i], __ldg(wr + i), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) job.d_out[(long long)b * job.cout + co] = rsqrtf(acc + 1e-8f);
+  for (int r = row0 + warp; r < min(row0 + SROWS, job.cout); r += 8) {
+    const float* wr = job.wsq + (long long)r * job.cin;
+    float acc[SB];
+#pragma unroll
+    for (int j = 0; j < SB; ++j) acc[j] = 0.f;
+    for (int k = lane; k < job.cin; k += 32) {
+      const float wv = __ldg(wr + k);
+#pragma unroll
+      for (int j = 0; j < SB; ++j) acc[j] = fmaf(ss[j * job.cin + k], wv, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < SB; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane < nb) {
+      float a = acc[0];
+#pragma unroll
+      for (int j = 1; j < SB; ++j) a = (lane == j) ? acc[j] : a;
+      job.d_out[(long long)(b0 + lane) * job.cout + r] = rsqrtf(a + 1e-8f);
+    }
   }
 }
 
@@ -125,10 +168,23 @@ extern "C" int maua_style_prologue_f32(const MauaStyleJob* jobs, int n_jobs, con
   MAUA_CHECK_ARG(jobs && latent && n_jobs >= 0 && batch >= 0, "style_prologue: bad arguments");
   MAUA_CHECK_ARG(style_dim >= 1 && style_dim <= 1024, "style_prologue: style_dim must be in [1,1024]");
   if (n_jobs == 0 || batch == 0) return MAUA_OK;
-  MAUA_CHECK_ARG(batch <= 65535, "style_prologue: batch too large");
-  style_prologue_kernel<<<dim3(n_jobs, batch), 256, 0, as_stream(stream)>>>(jobs, latent, mean, psi, psi_scalar,
-                                                                           latent_trunc_out, n_latent, style_dim);
-  MAUA_CHECK_LAUNCH("style_prologue");
+  const int max_dim = 1024;  // upper bound on cin / cout of a job (StyleGAN2: 512); rows beyond a job's size exit early
+  const int zb = ceil_div(batch, SB);
+  MAUA_CHECK_ARG(zb <= 65535, "style_prologue: batch too large");
+  cudaStream_t st = as_stream(stream);
+  const size_t smem_s = (size_t)SB * style_dim * sizeof(float);
+  const size_t smem_d = (size_t)SB * max_dim * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    MAUA_CHECK_CUDA(cudaFuncSetAttribute(style_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    MAUA_CHECK_CUDA(cudaFuncSetAttribute(style_d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_done = true;
+  }
+  style_s_kernel<<<dim3(n_jobs, max_dim / SROWS, zb), 256, smem_s, st>>>(jobs, latent, mean, psi, psi_scalar,
+                                                                        latent_trunc_out, batch, n_latent, style_dim);
+  MAUA_CHECK_LAUNCH("style_prologue(s)");
+  style_d_kernel<<<dim3(n_jobs, max_dim / SROWS, zb), 256, smem_d, st>>>(jobs, batch, max_dim);
+  MAUA_CHECK_LAUNCH("style_prologue(d)");
   return MAUA_OK;
 }
 

@@ -56,13 +56,23 @@ __global__ void __launch_bounds__(256) blur_tile_kernel(const float* __restrict_
   for (long long plane = blockIdx.y; plane < p.major; plane += gridDim.y) {
     const float* xp = x + plane * (long long)p.in_h * p.in_w;
     __syncthreads();  // previous iteration's readers are done (also orders skf)
-    for (int idx = tid; idx < ROWS * COLS; idx += 256) {
-      const int r = idx / COLS;
-      const int c = idx - r * COLS;
-      const int iy = iy0 + r, ix = ix0 + c;
-      float v = 0.f;
-      if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) v = __ldg(xp + (long long)iy * p.in_w + ix);
-      sx[r * PITCH + c] = v;
+    {
+      // row-per-warp staging: no integer division, one bounds test per row, coalesced 128-byte warp loads
+      const int lane = tid & 31, wrp = tid >> 5;
+#pragma unroll 1
+      for (int r = wrp; r < ROWS; r += 8) {
+        const int iy = iy0 + r;
+        const bool row_ok = (iy >= 0) && (iy < p.in_h);
+        const float* src = xp + (long long)iy * p.in_w + ix0;
+        float* dst = sx + r * PITCH;
+#pragma unroll
+        for (int c = lane; c < COLS; c += 32) {
+          const int ix = ix0 + c;
+          float v = 0.f;
+          if (row_ok && ix >= 0 && ix < p.in_w) v = __ldg(src + c);
+          dst[c] = v;
+        }
+      }
     }
     __syncthreads();
 
