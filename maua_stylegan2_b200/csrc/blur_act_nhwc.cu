@@ -207,11 +207,10 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_tma_kernel(const __grid_
         if (a >= 0 && a < 4) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float kv = kk[a * 4 + e];
-            acc[j].x = fmaf(row[e].x, kv, acc[j].x);
-            acc[j].y = fmaf(row[e].y, kv, acc[j].y);
-            acc[j].z = fmaf(row[e].z, kv, acc[j].z);
-            acc[j].w = fmaf(row[e].w, kv, acc[j].w);
+            const float2 kv = make_float2(kk[a * 4 + e], kk[a * 4 + e]);
+            const float2 lo2 = ffma2(make_float2(row[e].x, row[e].y), kv, make_float2(acc[j].x, acc[j].y));
+            const float2 hi2 = ffma2(make_float2(row[e].z, row[e].w), kv, make_float2(acc[j].z, acc[j].w));
+            acc[j] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
           }
         }
       }

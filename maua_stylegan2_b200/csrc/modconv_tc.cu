@@ -19,6 +19,7 @@
 // warps 2-5 = epilogue (tcgen05.ld 32 lanes x 16 columns, demod/noise/bias/lrelu/next-style/split, stores).
 // Two independent mbarrier rings (A tiles, B tiles) + one accumulator-full barrier.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -292,6 +293,12 @@ static int next_pow2(int v) {
 }  // namespace tc
 }  // namespace maua
 
+namespace maua {
+int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                       const MauaConvEpilogue& ep, int batch, int cin, int cout, int h, int w, int up, int n_products,
+                       cudaStream_t st);
+}
+
 extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                                const MauaConvEpilogue* ep_host, int batch, int cin, int cout, int h, int w, int up,
                                int n_products, void* stream) {
@@ -312,6 +319,14 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
     MAUA_CHECK_ARG(!ep.noise || ep.noise_weight, "modconv_tc: noise without noise_weight");
   }
   if (batch == 0) return MAUA_OK;
+
+  // halo variant (modconv_tc2.cu) wherever a 16x8 tile fits; v1 keeps the tiny (batch-folded) layers.
+  // MAUA_TC_V1=1 forces v1 everywhere (A/B measurements).
+  static const bool force_v1 = [] { const char* e = getenv("MAUA_TC_V1"); return e && e[0] == '1'; }();
+  if (!force_v1) {
+    const int rc2 = modconv_tc2_launch(x_hi, x_lo, w_hi, w_lo, ep, batch, cin, cout, h, w, up, n_products, as_stream(stream));
+    if (rc2 != MAUA_E_UNSUPPORTED) return rc2;
+  }
 
   Params p;
   p.B = batch; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout;

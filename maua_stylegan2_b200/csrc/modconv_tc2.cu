@@ -1,0 +1,365 @@
+// ModulatedConv2d 3x3 on tcgen05 — "halo" variant (v2): ONE activation load per K-chunk serves all 9 taps.
+//
+// v1 (modconv_tc.cu) issues one shifted TMA box per tap, so the A operand crosses L2->SMEM 9 times (4 times for the
+// transposed conv) and the ncu profile of round 1 shows the >=128^2 layers bound by L2->SM traffic, not by the tensor
+// pipe.  Here a CTA owns R vertically stacked tiles of 16 rows x 8 columns (M = 128 each).  Per K-chunk it loads the
+// (16R+2) x 10 pixel halo ONCE (4-D TMA box, zero padding = out-of-bounds fill) and every tap's A operand is just a
+// different START ADDRESS into that halo:   start = halo + ((r*16 + dy) * HW + dx) * row_bytes,   SBO = HW * row_bytes
+// (8 consecutive M rows = 8 consecutive pixels of one image row = contiguous shared-memory rows; the next 8-row group
+// is the next image row, one halo pitch further).  The 64B/128B swizzle is a function of absolute shared-memory address
+// bits, so TMA writes and UMMA reads stay consistent for any row offset and any group pitch (verified on B200 with
+// tools/exp_shifted_desc.cu).  The weight tile of a tap is loaded once and used by all R accumulators.
+// A traffic per output tile: (16R+2)*10 / (128R) = 1.3-1.4x instead of 9x; B traffic: 1/R.
+//
+// Everything else (split-bf16 3-product MMA, TMEM accumulators, epilogue fusion, sub-pixel phases for the transposed
+// conv) is as in v1.  Warp roles: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+#include "tmap.cuh"
+
+namespace maua {
+namespace tc2 {
+
+constexpr int TH = 16, TW = 8;  // one M tile = 16 rows x 8 columns
+
+struct Params {
+  int B, H, W, Cin, Cout;
+  int GH, GW;            // GEMM pixel grid: (H, W) same-res, (H+1, W+1) transposed
+  int R;                 // stacked M tiles per CTA
+  int HW_, HH_;          // halo width / height in pixels: same-res (10, 16R+2); up (9, 16R+1)
+  int tiles_x, tiles_y;  // tiles_y counts groups of R tiles
+  int BN, n_tiles;
+  int n_kchunks;
+  int SA, SB;
+  int nprod;
+  uint32_t a_plane;      // bytes of one bf16 plane of the halo, rounded up to 1024
+  uint32_t tmem_cols;
+};
+
+// tap -> (dy index, dx index, accumulator phase).  same-res: tap (ky,kx) reads x[y+ky-1, x+kx-1] -> halo (ky, kx).
+// transposed: u[2y'+py, 2x'+px] += W[ky,kx] * x[y'+dy, x'+dx], py = ky&1, dy = (ky==2 ? -1 : 0) -> halo row dy+1.
+struct Tap { int8_t hy, hx, phase, tap; };
+__constant__ Tap c_taps[2][9] = {
+    {{0, 0, 0, 0}, {0, 1, 0, 1}, {0, 2, 0, 2}, {1, 0, 0, 3}, {1, 1, 0, 4}, {1, 2, 0, 5}, {2, 0, 0, 6}, {2, 1, 0, 7}, {2, 2, 0, 8}},
+    {{1, 1, 0, 0}, {1, 1, 1, 1}, {1, 0, 0, 2}, {1, 1, 2, 3}, {1, 1, 3, 4}, {1, 0, 2, 5}, {0, 1, 0, 6}, {0, 1, 1, 7}, {0, 0, 0, 8}}};
+
+__device__ __forceinline__ float lrelu_s(float v, float slope, float scale) { return (v > 0.f ? v : v * slope) * scale; }
+
+template <int KC, bool UP>
+__global__ void __launch_bounds__(192, 1)
+modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                   const Params p, const MauaConvEpilogue ep) {
+  using namespace ptx;
+  constexpr uint32_t ROW = KC * 2;
+  constexpr int NPH = UP ? 4 : 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_stage = 2 * p.a_plane;
+  const uint32_t b_half = (uint32_t)p.BN * ROW, b_stage = 2 * b_half;
+  const uint32_t a_base = smem0;
+  const uint32_t b_base = a_base + (uint32_t)p.SA * a_stage;
+  const uint32_t bar_base = b_base + (uint32_t)p.SB * b_stage;
+  const uint32_t a_full = bar_base, a_empty = a_full + 8 * p.SA;
+  const uint32_t b_full = a_empty + 8 * p.SA, b_empty = b_full + 8 * p.SB;
+  const uint32_t acc_full = b_empty + 8 * p.SB;
+  const uint32_t tmem_slot = acc_full + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_tile = blockIdx.x / p.n_tiles;
+  const int tile_x = m_tile % p.tiles_x;
+  const int tile_y = (m_tile / p.tiles_x) % p.tiles_y;
+  const int b = m_tile / (p.tiles_x * p.tiles_y);
+  const int x0 = tile_x * TW, y0 = tile_y * TH * p.R, n0 = n_tile * p.BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a_hi);
+    prefetch_tmap(&tm_b_hi);
+    if (p.nprod > 1) {
+      prefetch_tmap(&tm_a_lo);
+      prefetch_tmap(&tm_b_lo);
+    }
+    for (int i = 0; i < p.SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const Tap* taps = c_taps[UP ? 1 : 0];
+  const uint32_t halo_bytes = (uint32_t)(p.HW_ * p.HH_) * ROW;  // bytes one TMA box writes per plane
+
+  if (warp == 0 && lane == 0) {
+    // ================================ TMA producer ================================
+    int ia = 0, ib = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int kc = 0; kc < p.n_kchunks; ++kc) {
+      const int c0 = kc * KC;
+      mbar_wait(a_empty + 8 * ia, pa ^ 1);
+      mbar_expect_tx(a_full + 8 * ia, halo_bytes * (p.nprod > 1 ? 2 : 1));
+      const uint32_t dst = a_base + ia * a_stage;
+      tma_load_4d(dst, &tm_a_hi, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
+      if (p.nprod > 1) tma_load_4d(dst + p.a_plane, &tm_a_lo, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
+      if (++ia == p.SA) { ia = 0; pa ^= 1; }
+#pragma unroll 1
+      for (int t = 0; t < 9; ++t) {
+        mbar_wait(b_empty + 8 * ib, pb ^ 1);
+        mbar_expect_tx(b_full + 8 * ib, p.nprod > 1 ? b_stage : b_half);
+        const uint32_t dstb = b_base + ib * b_stage;
+        tma_load_3d(dstb, &tm_b_hi, b_full + 8 * ib, c0, n0, taps[t].tap);
+        if (p.nprod > 1) tma_load_3d(dstb + b_half, &tm_b_lo, b_full + 8 * ib, c0, n0, taps[t].tap);
+        if (++ib == p.SB) { ib = 0; pb ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================================ MMA issuer ================================
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN);
+    const uint64_t sbo_field = (uint64_t)((((uint32_t)p.HW_ * ROW) >> 4) & 0x3FFF) << 32;
+    int ia = 0, ib = 0;
+    uint32_t pa = 0, pb = 0, started = 0;
+    for (int kc = 0; kc < p.n_kchunks; ++kc) {
+      mbar_wait(a_full + 8 * ia, pa);
+      const uint32_t a_hi = a_base + ia * a_stage, a_lo = a_hi + p.a_plane;
+#pragma unroll 1
+      for (int t = 0; t < 9; ++t) {
+        const Tap tp = taps[t];
+        mbar_wait(b_full + 8 * ib, pb);
+        tc_fence_after();
+        const uint32_t b_hi = b_base + ib * b_stage, b_lo = b_hi + b_half;
+#pragma unroll 1
+        for (int r = 0; r < p.R; ++r) {
+          const int acc_idx = tp.phase * p.R + r;
+          const uint32_t acc = tmem_base + (uint32_t)acc_idx * (uint32_t)p.BN;
+          const uint32_t a_off = (uint32_t)((r * TH + tp.hy) * p.HW_ + tp.hx) * ROW;
+          uint32_t accumulate = (started >> acc_idx) & 1u;
+#pragma unroll 1
+          for (int prod = 0; prod < p.nprod; ++prod) {
+            // K-major swizzled descriptor with a non-dense group pitch: SBO = halo pitch (see file header)
+            uint64_t da = make_kmajor_desc((prod == 2 ? a_lo : a_hi) + a_off, ROW);
+            da = (da & ~(0x3FFFull << 32)) | sbo_field;
+            const uint64_t db = make_kmajor_desc(prod == 1 ? b_lo : b_hi, ROW);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              umma_bf16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          started |= 1u << acc_idx;
+        }
+        umma_commit(b_empty + 8 * ib);
+        if (++ib == p.SB) { ib = 0; pb ^= 1; }
+      }
+      umma_commit(a_empty + 8 * ia);
+      if (++ia == p.SA) { ia = 0; pa ^= 1; }
+    }
+    umma_commit(acc_full);
+  } else if (warp >= 2) {
+    // ================================ epilogue ================================
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int tx = m & (TW - 1), ty = m >> 3;
+    const int gx = x0 + tx;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const float* dptr = ep.d ? ep.d + (long long)b * p.Cout + n0 : nullptr;
+    const float nwv = (!UP && ep.activate && ep.noise) ? __ldg(ep.noise_weight) : 0.f;
+#pragma unroll 1
+    for (int r = 0; r < p.R; ++r) {
+      const int gy = y0 + r * TH + ty;
+      const bool in_grid = (gy < p.GH) && (gx < p.GW);
+#pragma unroll 1
+      for (int ph = 0; ph < NPH; ++ph) {
+        int oy, ox, OH, OW;
+        bool valid;
+        if (UP) {
+          OH = 2 * p.H + 1; OW = 2 * p.W + 1;
+          oy = 2 * gy + (ph >> 1); ox = 2 * gx + (ph & 1);
+          valid = in_grid && oy < OH && ox < OW;
+        } else {
+          OH = p.H; OW = p.W; oy = gy; ox = gx; valid = in_grid;
+        }
+        const long long pix = valid ? (((long long)b * OH + oy) * OW + ox) : 0;
+        float nz = 0.f;
+        if (!UP && ep.activate && ep.noise && valid)
+          nz = nwv * __ldg(ep.noise + (long long)b * ep.noise_bstride + (long long)oy * OW + ox);
+        const uint32_t acc_col = (uint32_t)((ph * p.R + r) * p.BN);
+#pragma unroll 1
+        for (int c = 0; c < p.BN; c += 16) {
+          uint32_t rr[16];
+          tmem_ld_x16(lane_addr + acc_col + (uint32_t)c, rr);
+          tmem_ld_wait();
+          if (!valid) continue;
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = __uint_as_float(rr[i]);
+            if (dptr) v[i] *= __ldg(dptr + c + i);
+          }
+          if (UP) {
+            float4* dst = reinterpret_cast<float4*>(ep.out_raw_nhwc + pix * p.Cout + n0 + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            if (ep.activate) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float bb = ep.bias ? __ldg(ep.bias + n0 + c + i) : 0.f;
+                v[i] = lrelu_s((v[i] + nz) + bb, ep.slope, ep.act_scale);
+              }
+            }
+            if (ep.out_f32_nchw) {
+              float* dst = ep.out_f32_nchw + (((long long)b * p.Cout + n0 + c) * OH + oy) * OW + ox;
+              const long long plane = (long long)OH * OW;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) dst[i * plane] = v[i];
+            }
+            if (ep.out_hi) {
+              uint32_t h[8], l[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float s0 = 1.f, s1 = 1.f;
+                if (ep.s_next) {
+                  s0 = __ldg(ep.s_next + (long long)b * p.Cout + n0 + c + 2 * i);
+                  s1 = __ldg(ep.s_next + (long long)b * p.Cout + n0 + c + 2 * i + 1);
+                }
+                const float a0 = v[2 * i] * s0, a1 = v[2 * i + 1] * s1;
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
+                const float2 hf = __bfloat1622float2(hh);
+                const __nv_bfloat162 ll = __floats2bfloat162_rn(a0 - hf.x, a1 - hf.y);
+                h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+                l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+              }
+              uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_hi) + pix * p.Cout + n0 + c);
+              uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_lo) + pix * p.Cout + n0 + c);
+              dh[0] = make_uint4(h[0], h[1], h[2], h[3]);
+              dh[1] = make_uint4(h[4], h[5], h[6], h[7]);
+              dl[0] = make_uint4(l[0], l[1], l[2], l[3]);
+              dl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+static inline uint32_t align1k(uint32_t v) { return (v + 1023u) & ~1023u; }
+
+}  // namespace tc2
+
+// Returns MAUA_E_UNSUPPORTED when the shape is better served by v1 (tiny images: batch-folded tiles).
+int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                       const MauaConvEpilogue& ep, int batch, int cin, int cout, int h, int w, int up, int n_products,
+                       cudaStream_t st) {
+  using namespace tc2;
+  const int GH = up ? h + 1 : h, GW = up ? w + 1 : w;
+  if (GH < 4 * TH || GW < 4 * TW) return MAUA_E_UNSUPPORTED;  // <= 32^2: v1's batch-folded tiles fill the SMs better
+  Params p;
+  p.B = batch; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout; p.GH = GH; p.GW = GW;
+  const int nphase = up ? 4 : 1;
+  const int kc = 32;  // 64-byte operand rows: the halo of R = 4 stacked tiles still fits next to a deep B ring
+  const int n_kchunks = cin / kc;
+  const long long tiles_x = ceil_div(GW, TW);
+  const long long rows16 = ceil_div(GH, TH);
+  // Shallow layers (Cin <= 128: the >= 256^2 end of the network) have short K loops and are latency-bound per CTA:
+  // size them for two co-resident CTAs per SM (<= 256 TMEM columns, ~104 KB of shared memory each).
+  const bool two_ctas = cin <= 128;
+  const int tmem_cap = two_ctas ? 256 : 512;
+  const uint32_t budget = (two_ctas ? 104u : 208u) * 1024u;
+  // Pick (R, BN): minimise L2->SMEM bytes per tensor-pipe cycle,
+  //   bytes/cycle ~ [ (16R+2)*10/9 + BN ] / (R*BN)      (A halo amortised over 9 taps + one B tile per tap)
+  // subject to TMEM columns, shared memory (A halo + >= 2 B stages) and a grid that covers the 148 SMs.
+  int best_r = 0, best_bn = 0;
+  double best_cost = 1e30;
+  long long best_ctas = 0;
+  for (int r = 4; r >= 1; r >>= 1) {
+    if (r > rows16) continue;
+    for (int bn = 256; bn >= 16; bn >>= 1) {
+      if (cout % bn != 0 || r * nphase * bn > tmem_cap) continue;
+      const uint32_t plane = align1k((uint32_t)((TH * r + (up ? 1 : 2)) * (up ? TW + 1 : TW + 2) * kc * 2));
+      const uint32_t b_st = 2u * bn * kc * 2u;
+      if (2 * plane + 4 * b_st > budget) continue;  // A halo (hi+lo) + a B ring deep enough to hide TMA latency
+      const long long ctas = tiles_x * ceil_div(rows16, (long long)r) * batch * (cout / bn);
+      double cost = ((TH * r + 2) * 10.0 / 9.0 + bn) / ((double)r * bn);
+      if (bn < 32) cost *= 1.5;  // N = 16 leaves the MMA unit mostly idle
+      const bool enough = ctas >= 148, best_enough = best_ctas >= 148;
+      const bool better = best_r == 0 || (enough && !best_enough) || (enough == best_enough && (enough ? cost < best_cost : ctas > best_ctas));
+      if (better) { best_r = r; best_bn = bn; best_cost = cost; best_ctas = ctas; }
+    }
+  }
+  if (best_r == 0) return MAUA_E_UNSUPPORTED;
+  const int R = best_r, bn = best_bn;
+  p.R = R;
+  p.BN = bn;
+  p.n_tiles = cout / bn;
+  p.HW_ = up ? TW + 1 : TW + 2;
+  p.HH_ = TH * R + (up ? 1 : 2);
+  p.tiles_x = (int)tiles_x;
+  p.tiles_y = (int)ceil_div(rows16, (long long)R);
+  p.n_kchunks = n_kchunks;
+  p.nprod = n_products;
+  p.a_plane = align1k((uint32_t)(p.HW_ * p.HH_ * kc * 2));
+  int cols = 32;
+  while (cols < bn * nphase * R) cols <<= 1;
+  p.tmem_cols = (uint32_t)cols;
+  const uint32_t a_stage = 2 * p.a_plane, b_stage = 2u * bn * kc * 2u;
+  p.SA = (n_kchunks > 1 && 2 * a_stage + 3 * b_stage <= budget) ? 2 : 1;
+  int sb = (int)((budget - (uint32_t)p.SA * a_stage) / b_stage);
+  if (sb > 8) sb = 8;
+  if (sb < 2) return MAUA_E_UNSUPPORTED;
+  p.SB = sb;
+  const size_t smem = (size_t)p.SA * a_stage + (size_t)p.SB * b_stage + 8 * (2 * p.SA + 2 * p.SB + 2) + 1024;
+  if (smem > 227 * 1024) return MAUA_E_UNSUPPORTED;
+  const long long grid = tiles_x * p.tiles_y * batch * p.n_tiles;
+  if (grid >= (1LL << 31)) return MAUA_E_UNSUPPORTED;
+
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  const auto swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const cuuint64_t adims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+  const cuuint64_t astr[3] = {(cuuint64_t)cin * 2, (cuuint64_t)w * cin * 2, (cuuint64_t)h * w * cin * 2};
+  const cuuint32_t abox[4] = {(cuuint32_t)kc, (cuuint32_t)p.HW_, (cuuint32_t)p.HH_, 1};
+  const cuuint64_t bdims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
+  const cuuint64_t bstr[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
+  const cuuint32_t bbox[3] = {(cuuint32_t)kc, (cuuint32_t)bn, 1};
+  int rc;
+  if ((rc = tmap::encode(&ta_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x_hi, 4, adims, astr, abox, swz))) return rc;
+  if ((rc = tmap::encode(&tb_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_hi, 3, bdims, bstr, bbox, swz))) return rc;
+  if (n_products > 1) {
+    if ((rc = tmap::encode(&ta_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x_lo, 4, adims, astr, abox, swz))) return rc;
+    if ((rc = tmap::encode(&tb_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_lo, 3, bdims, bstr, bbox, swz))) return rc;
+  } else {
+    ta_lo = ta_hi;
+    tb_lo = tb_hi;
+  }
+#define MAUA_TC2_LAUNCH(KCV, UPV)                                                                                   \
+  do {                                                                                                              \
+    MAUA_CHECK_CUDA(cudaFuncSetAttribute(modconv_tc2_kernel<KCV, UPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                                               \
+    modconv_tc2_kernel<KCV, UPV><<<(unsigned)grid, 192, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep);             \
+  } while (0)
+  if (up) MAUA_TC2_LAUNCH(32, true); else MAUA_TC2_LAUNCH(32, false);
+#undef MAUA_TC2_LAUNCH
+  MAUA_CHECK_LAUNCH("modconv_tc(v2)");
+  return MAUA_OK;
+}
+
+}  // namespace maua

@@ -96,10 +96,14 @@ __global__ void __launch_bounds__(256) blur_tile_kernel(const float* __restrict_
       for (int j = 0; j < RY; ++j) {
         const int ky = r - j;
         if (ky >= 0 && ky < 4) {
+// outputs (0,1) and (2,3) advance together: two packed FMAs per tap, kx ascending per output (order kept)
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int kx = 0; kx < 4; ++kx) acc[j][i] = __fmaf_rn(row[i + kx], kf[ky * 4 + kx], acc[j][i]);
+          for (int kx = 0; kx < 4; ++kx) {
+            const float2 kv = make_float2(kf[ky * 4 + kx], kf[ky * 4 + kx]);
+            const float2 a01 = ffma2(make_float2(row[kx], row[kx + 1]), kv, make_float2(acc[j][0], acc[j][1]));
+            const float2 a23 = ffma2(make_float2(row[kx + 2], row[kx + 3]), kv, make_float2(acc[j][2], acc[j][3]));
+            acc[j][0] = a01.x; acc[j][1] = a01.y; acc[j][2] = a23.x; acc[j][3] = a23.y;
+          }
         }
       }
     }

@@ -20,7 +20,7 @@ using namespace maua::ptx;
 template <int KC>
 __global__ void __launch_bounds__(128, 1) exp_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                      const __grid_constant__ CUtensorMap tm_b, float* out, int R,
-                                                     int shift, int bo_mode) {
+                                                     int shift, int bo_mode, int pitch_rows) {
   constexpr uint32_t ROW = KC * 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(128, 1) exp_kernel(const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t a_start = a_smem + shift * ROW;
     uint64_t da = make_kmajor_desc(a_start, ROW);
+    da &= ~(0x3FFFull << 32);
+    da |= (uint64_t)(((uint32_t)pitch_rows * ROW) >> 4) << 32;  // SBO = pitch between 8-row groups
     uint64_t bo = 0;
     if (bo_mode == 1) bo = (a_start >> 7) & 7;
     if (bo_mode == 2) bo = (a_start / ROW) & 7;  // row index mod 8
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(128, 1) exp_kernel(const __grid_constant__ CUt
 static float bf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 template <int KC>
-int run(int R) {
+int run(int R, int pitch) {
   std::vector<__nv_bfloat16> A(R * KC), B(32 * KC);
   std::vector<float> Af(R * KC), Bf(32 * KC);
   srand(1);
@@ -103,11 +105,12 @@ int run(int R) {
   std::vector<float> O(128 * 32);
   const int shifts[] = {0, 1, 2, 3, 4, 5, 7, 8, 9, 16, 17, 65, 100};
   for (int mode = 0; mode < 3; ++mode) {
-    printf("KC=%d base_offset mode %d:", KC, mode);
+    if (mode != 0) continue;
+    printf("KC=%d pitch %d:", KC, pitch);
     for (int s : shifts) {
-      if (s + 128 > R) continue;
+      if (s + 15 * pitch + 8 > R) continue;
       cudaMemset(dO, 0, 128 * 32 * 4);
-      exp_kernel<KC><<<1, 128, smem>>>(ta, tb, dO, R, s, mode);
+      exp_kernel<KC><<<1, 128, smem>>>(ta, tb, dO, R, s, mode, pitch);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf(" [s=%d CUDA error %s]", s, cudaGetErrorString(e)); return 1; }
       cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost);
@@ -115,7 +118,7 @@ int run(int R) {
       for (int i = 0; i < 128; ++i)
         for (int n = 0; n < 32; ++n) {
           double ref = 0;
-          for (int k = 0; k < KC; ++k) ref += (double)Af[(s + i) * KC + k] * Bf[n * KC + k];
+          for (int k = 0; k < KC; ++k) ref += (double)Af[(s + (i / 8) * pitch + (i % 8)) * KC + k] * Bf[n * KC + k];
           maxerr = fmax(maxerr, fabs(ref - O[i * 32 + n]));
         }
       printf(" s=%d:%s(%.2g)", s, maxerr < 1e-3 ? "OK" : "BAD", maxerr);
@@ -126,7 +129,7 @@ int run(int R) {
 }
 
 int main() {
-  int rc = run<64>(232);
-  rc |= run<32>(232);
+  int rc = 0;
+  for (int pitch : {8, 9, 10, 17}) { rc |= run<64>(232, pitch); rc |= run<32>(232, pitch); }
   return rc;
 }
