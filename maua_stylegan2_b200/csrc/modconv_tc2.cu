@@ -14,6 +14,8 @@
 // Everything else (split-bf16 3-product MMA, TMEM accumulators, epilogue fusion, sub-pixel phases for the transposed
 // conv) is as in v1.  Warp roles: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue.
 #include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -36,6 +38,8 @@ struct Params {
   int nprod;
   uint32_t a_plane;      // bytes of one bf16 plane of the halo, rounded up to 1024
   uint32_t tmem_cols;
+  int AS;                // TMEM accumulator stages (2 = epilogue of item i overlaps the MMAs of item i+1)
+  int n_items;           // work items = n_tiles * tiles_x * tiles_y * B, walked persistently with stride gridDim.x
 };
 
 // tap -> (dy index, dx index, accumulator phase).  same-res: tap (ky,kx) reads x[y+ky-1, x+kx-1] -> halo (ky, kx).
@@ -64,16 +68,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const uint32_t bar_base = b_base + (uint32_t)p.SB * b_stage;
   const uint32_t a_full = bar_base, a_empty = a_full + 8 * p.SA;
   const uint32_t b_full = a_empty + 8 * p.SA, b_empty = b_full + 8 * p.SB;
-  const uint32_t acc_full = b_empty + 8 * p.SB;
-  const uint32_t tmem_slot = acc_full + 8;
+  const uint32_t acc_full = b_empty + 8 * p.SB, acc_empty = acc_full + 8 * p.AS;
+  const uint32_t tmem_slot = acc_empty + 8 * p.AS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  const int n_tile = blockIdx.x % p.n_tiles;
-  const int m_tile = blockIdx.x / p.n_tiles;
-  const int tile_x = m_tile % p.tiles_x;
-  const int tile_y = (m_tile / p.tiles_x) % p.tiles_y;
-  const int b = m_tile / (p.tiles_x * p.tiles_y);
-  const int x0 = tile_x * TW, y0 = tile_y * TH * p.R, n0 = n_tile * p.BN;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi);
@@ -84,7 +81,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
     for (int i = 0; i < p.SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < p.AS; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -97,6 +94,17 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // work item -> tile coordinates (n fastest: CTAs running concurrently share the activation halo through L2)
+  auto decode = [&](int item, int& n0, int& x0, int& y0, int& b) {
+    const int n_tile = item % p.n_tiles;
+    const int m_tile = item / p.n_tiles;
+    x0 = (m_tile % p.tiles_x) * TW;
+    y0 = ((m_tile / p.tiles_x) % p.tiles_y) * TH * p.R;
+    b = m_tile / (p.tiles_x * p.tiles_y);
+    n0 = n_tile * p.BN;
+  };
+  const uint32_t acc_cols = (uint32_t)(NPH * p.R * p.BN);  // TMEM columns of one accumulator stage
+
   const Tap* taps = c_taps[UP ? 1 : 0];
   const uint32_t halo_bytes = (uint32_t)(p.HW_ * p.HH_) * ROW;  // bytes one TMA box writes per plane
 
@@ -104,77 +112,93 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     // ================================ TMA producer ================================
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
-    for (int kc = 0; kc < p.n_kchunks; ++kc) {
-      const int c0 = kc * KC;
-      mbar_wait(a_empty + 8 * ia, pa ^ 1);
-      mbar_expect_tx(a_full + 8 * ia, halo_bytes * (p.nprod > 1 ? 2 : 1));
-      const uint32_t dst = a_base + ia * a_stage;
-      tma_load_4d(dst, &tm_a_hi, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
-      if (p.nprod > 1) tma_load_4d(dst + p.a_plane, &tm_a_lo, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
-      if (++ia == p.SA) { ia = 0; pa ^= 1; }
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      int n0, x0, y0, b;
+      decode(item, n0, x0, y0, b);
+      for (int kc = 0; kc < p.n_kchunks; ++kc) {
+        const int c0 = kc * KC;
+        mbar_wait(a_empty + 8 * ia, pa ^ 1);
+        mbar_expect_tx(a_full + 8 * ia, halo_bytes * (p.nprod > 1 ? 2 : 1));
+        const uint32_t dst = a_base + ia * a_stage;
+        tma_load_4d(dst, &tm_a_hi, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
+        if (p.nprod > 1) tma_load_4d(dst + p.a_plane, &tm_a_lo, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
+        if (++ia == p.SA) { ia = 0; pa ^= 1; }
 #pragma unroll 1
-      for (int t = 0; t < 9; ++t) {
-        mbar_wait(b_empty + 8 * ib, pb ^ 1);
-        mbar_expect_tx(b_full + 8 * ib, p.nprod > 1 ? b_stage : b_half);
-        const uint32_t dstb = b_base + ib * b_stage;
-        tma_load_3d(dstb, &tm_b_hi, b_full + 8 * ib, c0, n0, taps[t].tap);
-        if (p.nprod > 1) tma_load_3d(dstb + b_half, &tm_b_lo, b_full + 8 * ib, c0, n0, taps[t].tap);
-        if (++ib == p.SB) { ib = 0; pb ^= 1; }
+        for (int t = 0; t < 9; ++t) {
+          mbar_wait(b_empty + 8 * ib, pb ^ 1);
+          mbar_expect_tx(b_full + 8 * ib, p.nprod > 1 ? b_stage : b_half);
+          const uint32_t dstb = b_base + ib * b_stage;
+          tma_load_3d(dstb, &tm_b_hi, b_full + 8 * ib, c0, n0, taps[t].tap);
+          if (p.nprod > 1) tma_load_3d(dstb + b_half, &tm_b_lo, b_full + 8 * ib, c0, n0, taps[t].tap);
+          if (++ib == p.SB) { ib = 0; pb ^= 1; }
+        }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ================================ MMA issuer ================================
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN);
     const uint64_t sbo_field = (uint64_t)((((uint32_t)p.HW_ * ROW) >> 4) & 0x3FFF) << 32;
-    int ia = 0, ib = 0;
-    uint32_t pa = 0, pb = 0, started = 0;
-    for (int kc = 0; kc < p.n_kchunks; ++kc) {
-      mbar_wait(a_full + 8 * ia, pa);
-      const uint32_t a_hi = a_base + ia * a_stage, a_lo = a_hi + p.a_plane;
+    int ia = 0, ib = 0, as = 0;
+    uint32_t pa = 0, pb = 0, pacc = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      mbar_wait(acc_empty + 8 * as, pacc ^ 1);  // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t acc_stage = tmem_base + (uint32_t)as * acc_cols;
+      uint32_t started = 0;
+      for (int kc = 0; kc < p.n_kchunks; ++kc) {
+        mbar_wait(a_full + 8 * ia, pa);
+        const uint32_t a_hi = a_base + ia * a_stage, a_lo = a_hi + p.a_plane;
 #pragma unroll 1
-      for (int t = 0; t < 9; ++t) {
-        const Tap tp = taps[t];
-        mbar_wait(b_full + 8 * ib, pb);
-        tc_fence_after();
-        const uint32_t b_hi = b_base + ib * b_stage, b_lo = b_hi + b_half;
+        for (int t = 0; t < 9; ++t) {
+          const Tap tp = taps[t];
+          mbar_wait(b_full + 8 * ib, pb);
+          tc_fence_after();
+          const uint32_t b_hi = b_base + ib * b_stage, b_lo = b_hi + b_half;
 #pragma unroll 1
-        for (int r = 0; r < p.R; ++r) {
-          const int acc_idx = tp.phase * p.R + r;
-          const uint32_t acc = tmem_base + (uint32_t)acc_idx * (uint32_t)p.BN;
-          const uint32_t a_off = (uint32_t)((r * TH + tp.hy) * p.HW_ + tp.hx) * ROW;
-          uint32_t accumulate = (started >> acc_idx) & 1u;
+          for (int r = 0; r < p.R; ++r) {
+            const int acc_idx = tp.phase * p.R + r;
+            const uint32_t acc = acc_stage + (uint32_t)acc_idx * (uint32_t)p.BN;
+            const uint32_t a_off = (uint32_t)((r * TH + tp.hy) * p.HW_ + tp.hx) * ROW;
+            uint32_t accumulate = (started >> acc_idx) & 1u;
 #pragma unroll 1
-          for (int prod = 0; prod < p.nprod; ++prod) {
-            // K-major swizzled descriptor with a non-dense group pitch: SBO = halo pitch (see file header)
-            uint64_t da = make_kmajor_desc((prod == 2 ? a_lo : a_hi) + a_off, ROW);
-            da = (da & ~(0x3FFFull << 32)) | sbo_field;
-            const uint64_t db = make_kmajor_desc(prod == 1 ? b_lo : b_hi, ROW);
+            for (int prod = 0; prod < p.nprod; ++prod) {
+              // K-major swizzled descriptor with a non-dense group pitch: SBO = halo pitch (see file header)
+              uint64_t da = make_kmajor_desc((prod == 2 ? a_lo : a_hi) + a_off, ROW);
+              da = (da & ~(0x3FFFull << 32)) | sbo_field;
+              const uint64_t db = make_kmajor_desc(prod == 1 ? b_lo : b_hi, ROW);
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k) {
-              umma_bf16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
-              accumulate = 1;
+              for (int k = 0; k < KC / 16; ++k) {
+                umma_bf16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
+                accumulate = 1;
+              }
             }
+            started |= 1u << acc_idx;
           }
-          started |= 1u << acc_idx;
+          umma_commit(b_empty + 8 * ib);
+          if (++ib == p.SB) { ib = 0; pb ^= 1; }
         }
-        umma_commit(b_empty + 8 * ib);
-        if (++ib == p.SB) { ib = 0; pb ^= 1; }
+        umma_commit(a_empty + 8 * ia);
+        if (++ia == p.SA) { ia = 0; pa ^= 1; }
       }
-      umma_commit(a_empty + 8 * ia);
-      if (++ia == p.SA) { ia = 0; pa ^= 1; }
+      umma_commit(acc_full + 8 * as);
+      if (++as == p.AS) { as = 0; pacc ^= 1; }
     }
-    umma_commit(acc_full);
   } else if (warp >= 2) {
     // ================================ epilogue ================================
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
     const int tx = m & (TW - 1), ty = m >> 3;
-    const int gx = x0 + tx;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const float* dptr = ep.d ? ep.d + (long long)b * p.Cout + n0 : nullptr;
     const float nwv = (!UP && ep.activate && ep.noise) ? __ldg(ep.noise_weight) : 0.f;
+    int as = 0;
+    uint32_t pacc = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    int n0, x0, y0, b;
+    decode(item, n0, x0, y0, b);
+    const int gx = x0 + tx;
+    mbar_wait(acc_full + 8 * as, pacc);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * acc_cols;
+    const float* dptr = ep.d ? ep.d + (long long)b * p.Cout + n0 : nullptr;
 #pragma unroll 1
     for (int r = 0; r < p.R; ++r) {
       const int gy = y0 + r * TH + ty;
@@ -252,6 +276,12 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       }
     }
+      // accumulator stage drained: hand it back to the MMA issuer
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+    if (++as == p.AS) { as = 0; pacc ^= 1; }
+    }
   }
 
   tc_fence_before();
@@ -280,11 +310,10 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   const int n_kchunks = cin / kc;
   const long long tiles_x = ceil_div(GW, TW);
   const long long rows16 = ceil_div(GH, TH);
-  // Shallow layers (Cin <= 128: the >= 256^2 end of the network) have short K loops and are latency-bound per CTA:
-  // size them for two co-resident CTAs per SM (<= 256 TMEM columns, ~104 KB of shared memory each).
-  const bool two_ctas = cin <= 128;
-  const int tmem_cap = two_ctas ? 256 : 512;
-  const uint32_t budget = (two_ctas ? 104u : 208u) * 1024u;
+  // Persistent kernel: one CTA per SM owns the whole shared memory (deep rings) and all 512 TMEM columns; when two
+  // accumulator stages fit (2*R*nphase*BN <= 512) the epilogue of item i overlaps the MMAs of item i+1.
+  const int tmem_cap = 512;
+  const uint32_t budget = 212u * 1024u;
   // Pick (R, BN): minimise L2->SMEM bytes per tensor-pipe cycle,
   //   bytes/cycle ~ [ (16R+2)*10/9 + BN ] / (R*BN)      (A halo amortised over 9 taps + one B tile per tap)
   // subject to TMEM columns, shared memory (A halo + >= 2 B stages) and a grid that covers the 148 SMs.
@@ -299,9 +328,12 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
       const uint32_t b_st = 2u * bn * kc * 2u;
       if (2 * plane + 4 * b_st > budget) continue;  // A halo (hi+lo) + a B ring deep enough to hide TMA latency
       const long long ctas = tiles_x * ceil_div(rows16, (long long)r) * batch * (cout / bn);
-      double cost = ((TH * r + 2) * 10.0 / 9.0 + bn) / ((double)r * bn);
-      if (bn < 32) cost *= 1.5;  // N = 16 leaves the MMA unit mostly idle
-      const bool enough = ctas >= 148, best_enough = best_ctas >= 148;
+      // modelled tensor-pipe cycles per MMA of N columns: max(math N/2, operand fetch (4 KB A + 32N B) / 128 B/clk);
+      // single accumulator stage => the epilogue is exposed (penalty); L2->SMEM bytes per cycle as a tie-breaker
+      const double mma_cyc = (bn / 2.0 > 32.0 + bn / 4.0 ? bn / 2.0 : 32.0 + bn / 4.0) / bn;
+      const double traffic = ((TH * r + 2) * 10.0 / 9.0 + bn) / ((double)r * bn);
+      double cost = mma_cyc * (2 * r * nphase * bn <= 512 ? 1.0 : 1.35) + 0.05 * traffic;
+      const bool enough = ctas >= 2 * 148, best_enough = best_ctas >= 2 * 148;
       const bool better = best_r == 0 || (enough && !best_enough) || (enough == best_enough && (enough ? cost < best_cost : ctas > best_ctas));
       if (better) { best_r = r; best_bn = bn; best_cost = cost; best_ctas = ctas; }
     }
@@ -322,15 +354,31 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   while (cols < bn * nphase * R) cols <<= 1;
   p.tmem_cols = (uint32_t)cols;
   const uint32_t a_stage = 2 * p.a_plane, b_stage = 2u * bn * kc * 2u;
-  p.SA = (n_kchunks > 1 && 2 * a_stage + 3 * b_stage <= budget) ? 2 : 1;
+  p.SA = (2 * a_stage + 4 * b_stage <= budget) ? 2 : 1;
   int sb = (int)((budget - (uint32_t)p.SA * a_stage) / b_stage);
-  if (sb > 8) sb = 8;
+  if (sb > 12) sb = 12;
   if (sb < 2) return MAUA_E_UNSUPPORTED;
   p.SB = sb;
-  const size_t smem = (size_t)p.SA * a_stage + (size_t)p.SB * b_stage + 8 * (2 * p.SA + 2 * p.SB + 2) + 1024;
+  const size_t smem = (size_t)p.SA * a_stage + (size_t)p.SB * b_stage + 8 * (2 * p.SA + 2 * p.SB + 6) + 1024;
   if (smem > 227 * 1024) return MAUA_E_UNSUPPORTED;
-  const long long grid = tiles_x * p.tiles_y * batch * p.n_tiles;
-  if (grid >= (1LL << 31)) return MAUA_E_UNSUPPORTED;
+  const long long items = tiles_x * p.tiles_y * batch * p.n_tiles;
+  if (items >= (1LL << 31)) return MAUA_E_UNSUPPORTED;
+  p.n_items = (int)items;
+  p.AS = (2 * bn * nphase * R <= 512) ? 2 : 1;
+  cols = 32;
+  while (cols < p.AS * bn * nphase * R) cols <<= 1;
+  p.tmem_cols = (uint32_t)cols;
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  }
+  const long long grid = items < n_sm ? items : n_sm;
+  static const bool debug = [] { const char* e = getenv("MAUA_TC_DEBUG"); return e && e[0] == '1'; }();
+  if (debug)
+    fprintf(stderr, "[modconv_tc2] %s B%d %d->%d @%dx%d: R=%d BN=%d AS=%d SA=%d SB=%d smem=%zuKB tmem=%u items=%lld grid=%lld\n",
+            up ? "up" : "same", batch, cin, cout, h, w, R, bn, p.AS, p.SA, p.SB, smem / 1024, p.tmem_cols, items, grid);
 
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   const auto swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
