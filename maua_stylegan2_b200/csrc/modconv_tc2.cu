@@ -25,6 +25,8 @@ namespace maua {
 namespace tc2 {
 
 constexpr int TH = 16, TW = 8;  // one M tile = 16 rows x 8 columns
+constexpr int EPI_GROUPS = 3;   // epilogue warps = 4 * EPI_GROUPS (each TMEM lane quadrant is served by EPI_GROUPS warps)
+constexpr int THREADS = 64 + 128 * EPI_GROUPS;
 
 struct Params {
   int B, H, W, Cin, Cout;
@@ -52,7 +54,7 @@ __constant__ Tap c_taps[2][9] = {
 __device__ __forceinline__ float lrelu_s(float v, float slope, float scale) { return (v > 0.f ? v : v * slope) * scale; }
 
 template <int KC, bool UP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(THREADS, 1)
 modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const Params p, const MauaConvEpilogue ep) {
@@ -81,7 +83,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
     for (int i = 0; i < p.SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    for (int i = 0; i < p.AS; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
+    for (int i = 0; i < p.AS; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4 * EPI_GROUPS); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -185,7 +187,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
   } else if (warp >= 2) {
     // ================================ epilogue ================================
+    // 4*EPI_GROUPS warps: warp w serves TMEM lane quadrant (w & 3); the 16-column chunks of all accumulators of an
+    // item are dealt round-robin to the EPI_GROUPS warps of a quadrant (a lone warp per scheduler exposes every latency)
     const int quad = warp & 3;
+    const int egroup = (warp - 2) >> 2;
     const int m = quad * 32 + lane;
     const int tx = m & (TW - 1), ty = m >> 3;
     const float nwv = (!UP && ep.activate && ep.noise) ? __ldg(ep.noise_weight) : 0.f;
@@ -221,15 +226,24 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const uint32_t acc_col = (uint32_t)((ph * p.R + r) * p.BN);
 #pragma unroll 1
         for (int c = 0; c < p.BN; c += 16) {
+          if ((((ph * p.R + r) * p.BN + c) >> 4) % EPI_GROUPS != egroup) continue;  // warp-uniform
           uint32_t rr[16];
           tmem_ld_x16(lane_addr + acc_col + (uint32_t)c, rr);
           tmem_ld_wait();
           if (!valid) continue;
           float v[16];
+          if (dptr) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = __uint_as_float(rr[i]);
-            if (dptr) v[i] *= __ldg(dptr + c + i);
+            for (int q = 0; q < 4; ++q) {
+              const float4 dv = __ldg(reinterpret_cast<const float4*>(dptr + c) + q);
+              v[4 * q] = __uint_as_float(rr[4 * q]) * dv.x;
+              v[4 * q + 1] = __uint_as_float(rr[4 * q + 1]) * dv.y;
+              v[4 * q + 2] = __uint_as_float(rr[4 * q + 2]) * dv.z;
+              v[4 * q + 3] = __uint_as_float(rr[4 * q + 3]) * dv.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
           }
           if (UP) {
             float4* dst = reinterpret_cast<float4*>(ep.out_raw_nhwc + pix * p.Cout + n0 + c);
@@ -238,9 +252,13 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           } else {
             if (ep.activate) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float bb = ep.bias ? __ldg(ep.bias + n0 + c + i) : 0.f;
-                v[i] = lrelu_s((v[i] + nz) + bb, ep.slope, ep.act_scale);
+              for (int q = 0; q < 4; ++q) {
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ep.bias) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c) + q);
+                v[4 * q] = lrelu_s((v[4 * q] + nz) + bv.x, ep.slope, ep.act_scale);
+                v[4 * q + 1] = lrelu_s((v[4 * q + 1] + nz) + bv.y, ep.slope, ep.act_scale);
+                v[4 * q + 2] = lrelu_s((v[4 * q + 2] + nz) + bv.z, ep.slope, ep.act_scale);
+                v[4 * q + 3] = lrelu_s((v[4 * q + 3] + nz) + bv.w, ep.slope, ep.act_scale);
               }
             }
             if (ep.out_f32_nchw) {
@@ -251,14 +269,16 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             }
             if (ep.out_hi) {
               uint32_t h[8], l[8];
+              float sn[16];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float4 sv = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (ep.s_next) sv = __ldg(reinterpret_cast<const float4*>(ep.s_next + (long long)b * p.Cout + n0 + c) + q);
+                sn[4 * q] = sv.x; sn[4 * q + 1] = sv.y; sn[4 * q + 2] = sv.z; sn[4 * q + 3] = sv.w;
+              }
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                float s0 = 1.f, s1 = 1.f;
-                if (ep.s_next) {
-                  s0 = __ldg(ep.s_next + (long long)b * p.Cout + n0 + c + 2 * i);
-                  s1 = __ldg(ep.s_next + (long long)b * p.Cout + n0 + c + 2 * i + 1);
-                }
-                const float a0 = v[2 * i] * s0, a1 = v[2 * i + 1] * s1;
+                const float a0 = v[2 * i] * sn[2 * i], a1 = v[2 * i + 1] * sn[2 * i + 1];
                 const __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
                 const float2 hf = __bfloat1622float2(hh);
                 const __nv_bfloat162 ll = __floats2bfloat162_rn(a0 - hf.x, a1 - hf.y);
@@ -402,7 +422,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   do {                                                                                                              \
     MAUA_CHECK_CUDA(cudaFuncSetAttribute(modconv_tc2_kernel<KCV, UPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem));                                                               \
-    modconv_tc2_kernel<KCV, UPV><<<(unsigned)grid, 192, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep);             \
+    modconv_tc2_kernel<KCV, UPV><<<(unsigned)grid, THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep);             \
   } while (0)
   if (up) MAUA_TC2_LAUNCH(32, true); else MAUA_TC2_LAUNCH(32, false);
 #undef MAUA_TC2_LAUNCH
