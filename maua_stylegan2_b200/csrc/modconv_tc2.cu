@@ -61,6 +61,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   using namespace ptx;
   constexpr uint32_t ROW = KC * 2;
   constexpr int NPH = UP ? 4 : 1;
+  static_assert(KC == 32, "the issue loop below is written for two K=16 steps per chunk");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_stage = 2 * p.a_plane;
@@ -138,8 +139,16 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
   } else if (warp == 1 && lane == 0) {
     // ================================ MMA issuer ================================
+    // The issue loop must stay far below the ~50 cycles a 128x32x16 MMA occupies the tensor pipe: all descriptor
+    // fields are folded into per-stage base values up front; per MMA only 64-bit adds of small constants remain.
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN);
     const uint64_t sbo_field = (uint64_t)((((uint32_t)p.HW_ * ROW) >> 4) & 0x3FFF) << 32;
+    const uint64_t da0 = (make_kmajor_desc(a_base, ROW) & ~(0x3FFFull << 32)) | sbo_field;  // A stage 0, hi plane
+    const uint64_t db0 = make_kmajor_desc(b_base, ROW);                                      // B stage 0, hi plane
+    const uint64_t a_stage16 = a_stage >> 4, a_plane16 = p.a_plane >> 4;
+    const uint64_t b_stage16 = b_stage >> 4, b_half16 = b_half >> 4;
+    const uint32_t rstep16 = (uint32_t)(TH * p.HW_) * ROW >> 4;  // next stacked tile: 16 halo rows further
+    const bool three = p.nprod > 1;
     int ia = 0, ib = 0, as = 0;
     uint32_t pa = 0, pb = 0, pacc = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -149,33 +158,31 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       uint32_t started = 0;
       for (int kc = 0; kc < p.n_kchunks; ++kc) {
         mbar_wait(a_full + 8 * ia, pa);
-        const uint32_t a_hi = a_base + ia * a_stage, a_lo = a_hi + p.a_plane;
+        const uint64_t da_stage = da0 + (uint64_t)ia * a_stage16;
 #pragma unroll 1
         for (int t = 0; t < 9; ++t) {
           const Tap tp = taps[t];
           mbar_wait(b_full + 8 * ib, pb);
           tc_fence_after();
-          const uint32_t b_hi = b_base + ib * b_stage, b_lo = b_hi + b_half;
+          const uint64_t dbh = db0 + (uint64_t)ib * b_stage16, dbl = dbh + b_half16;
+          uint64_t dah = da_stage + (uint64_t)((uint32_t)(tp.hy * p.HW_ + tp.hx) * ROW >> 4);
+          uint32_t acc = acc_stage + (uint32_t)(tp.phase * p.R) * (uint32_t)p.BN;
+          const uint32_t first = ((started >> tp.phase) & 1u);  // all R accumulators of a phase start together
 #pragma unroll 1
           for (int r = 0; r < p.R; ++r) {
-            const int acc_idx = tp.phase * p.R + r;
-            const uint32_t acc = acc_stage + (uint32_t)acc_idx * (uint32_t)p.BN;
-            const uint32_t a_off = (uint32_t)((r * TH + tp.hy) * p.HW_ + tp.hx) * ROW;
-            uint32_t accumulate = (started >> acc_idx) & 1u;
-#pragma unroll 1
-            for (int prod = 0; prod < p.nprod; ++prod) {
-              // K-major swizzled descriptor with a non-dense group pitch: SBO = halo pitch (see file header)
-              uint64_t da = make_kmajor_desc((prod == 2 ? a_lo : a_hi) + a_off, ROW);
-              da = (da & ~(0x3FFFull << 32)) | sbo_field;
-              const uint64_t db = make_kmajor_desc(prod == 1 ? b_lo : b_hi, ROW);
-#pragma unroll
-              for (int k = 0; k < KC / 16; ++k) {
-                umma_bf16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
-                accumulate = 1;
-              }
+            const uint64_t dal = dah + a_plane16;
+            umma_bf16(acc, dah, dbh, idesc, first);
+            umma_bf16(acc, dah + 2, dbh + 2, idesc, 1u);
+            if (three) {
+              umma_bf16(acc, dah, dbl, idesc, 1u);
+              umma_bf16(acc, dah + 2, dbl + 2, idesc, 1u);
+              umma_bf16(acc, dal, dbh, idesc, 1u);
+              umma_bf16(acc, dal + 2, dbh + 2, idesc, 1u);
             }
-            started |= 1u << acc_idx;
+            dah += rstep16;
+            acc += (uint32_t)p.BN;
           }
+          started |= 1u << tp.phase;
           umma_commit(b_empty + 8 * ib);
           if (++ib == p.SB) { ib = 0; pb ^= 1; }
         }
