@@ -38,18 +38,25 @@ struct Params {
   int n_kchunks;
   int SA, SB;
   int nprod;
+  int cat;               // 1: hi*[hi|lo] as ONE MMA of N = 2*BN plus lo*hi (2 MMAs per K-step instead of 3)
   uint32_t a_plane;      // bytes of one bf16 plane of the halo, rounded up to 1024
   uint32_t tmem_cols;
   int AS;                // TMEM accumulator stages (2 = epilogue of item i overlaps the MMAs of item i+1)
-  int n_items;           // work items = n_tiles * tiles_x * tiles_y * B, walked persistently with stride gridDim.x
+  int n_phase;           // 1 same-res, 4 transposed (each sub-pixel phase is its own work item)
+  int n_items;           // work items = n_tiles * n_phase * tiles_x * tiles_y * B, walked with stride gridDim.x
 };
 
-// tap -> (dy index, dx index, accumulator phase).  same-res: tap (ky,kx) reads x[y+ky-1, x+kx-1] -> halo (ky, kx).
-// transposed: u[2y'+py, 2x'+px] += W[ky,kx] * x[y'+dy, x'+dx], py = ky&1, dy = (ky==2 ? -1 : 0) -> halo row dy+1.
-struct Tap { int8_t hy, hx, phase, tap; };
-__constant__ Tap c_taps[2][9] = {
-    {{0, 0, 0, 0}, {0, 1, 0, 1}, {0, 2, 0, 2}, {1, 0, 0, 3}, {1, 1, 0, 4}, {1, 2, 0, 5}, {2, 0, 0, 6}, {2, 1, 0, 7}, {2, 2, 0, 8}},
-    {{1, 1, 0, 0}, {1, 1, 1, 1}, {1, 0, 0, 2}, {1, 1, 2, 3}, {1, 1, 3, 4}, {1, 0, 2, 5}, {0, 1, 0, 6}, {0, 1, 1, 7}, {0, 0, 0, 8}}};
+// Tap lists.  same-res: tap (ky,kx) reads x[y+ky-1, x+kx-1] -> halo (ky, kx).
+// transposed: u[2y'+py, 2x'+px] += W[ky,kx] * x[y'+dy, x'+dx], py = ky&1, dy = (ky==2 ? -1 : 0) -> halo row dy+1;
+// phase (py,px) owns the taps with ky&1 == py and kx&1 == px: 4 / 2 / 2 / 1 taps.
+struct Tap { int8_t hy, hx, tap, pad; };
+struct TapList { int32_t n; Tap t[9]; };
+__constant__ TapList c_taps[5] = {
+    {9, {{0, 0, 0, 0}, {0, 1, 1, 0}, {0, 2, 2, 0}, {1, 0, 3, 0}, {1, 1, 4, 0}, {1, 2, 5, 0}, {2, 0, 6, 0}, {2, 1, 7, 0}, {2, 2, 8, 0}}},
+    {4, {{1, 1, 0, 0}, {1, 0, 2, 0}, {0, 1, 6, 0}, {0, 0, 8, 0}}},  // phase 0: (0,0) (0,2) (2,0) (2,2)
+    {2, {{1, 1, 1, 0}, {0, 1, 7, 0}}},                              // phase 1: (0,1) (2,1)
+    {2, {{1, 1, 3, 0}, {1, 0, 5, 0}}},                              // phase 2: (1,0) (1,2)
+    {1, {{1, 1, 4, 0}}}};                                           // phase 3: (1,1)
 
 __device__ __forceinline__ float lrelu_s(float v, float slope, float scale) { return (v > 0.f ? v : v * slope) * scale; }
 
@@ -60,7 +67,6 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                    const Params p, const MauaConvEpilogue ep) {
   using namespace ptx;
   constexpr uint32_t ROW = KC * 2;
-  constexpr int NPH = UP ? 4 : 1;
   static_assert(KC == 32, "the issue loop below is written for two K=16 steps per chunk");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -97,27 +103,30 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // work item -> tile coordinates (n fastest: CTAs running concurrently share the activation halo through L2)
-  auto decode = [&](int item, int& n0, int& x0, int& y0, int& b) {
+  // work item -> (n tile, phase, pixel tile); n fastest, then phase: concurrently running CTAs share the activation
+  // halo through L2
+  auto decode = [&](int item, int& n0, int& ph, int& x0, int& y0, int& b) {
     const int n_tile = item % p.n_tiles;
-    const int m_tile = item / p.n_tiles;
-    x0 = (m_tile % p.tiles_x) * TW;
-    y0 = ((m_tile / p.tiles_x) % p.tiles_y) * TH * p.R;
-    b = m_tile / (p.tiles_x * p.tiles_y);
+    int rest = item / p.n_tiles;
+    ph = rest % p.n_phase;
+    rest /= p.n_phase;
+    x0 = (rest % p.tiles_x) * TW;
+    y0 = ((rest / p.tiles_x) % p.tiles_y) * TH * p.R;
+    b = rest / (p.tiles_x * p.tiles_y);
     n0 = n_tile * p.BN;
   };
-  const uint32_t acc_cols = (uint32_t)(NPH * p.R * p.BN);  // TMEM columns of one accumulator stage
-
-  const Tap* taps = c_taps[UP ? 1 : 0];
-  const uint32_t halo_bytes = (uint32_t)(p.HW_ * p.HH_) * ROW;  // bytes one TMA box writes per plane
+  const uint32_t blk_cols = (uint32_t)(p.cat ? 2 * p.BN : p.BN);  // TMEM columns of one accumulator
+  const uint32_t acc_cols = (uint32_t)p.R * blk_cols;             // ... of one accumulator stage
+  const uint32_t halo_bytes = (uint32_t)(p.HW_ * p.HH_) * ROW;    // bytes one TMA box writes per plane
 
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer ================================
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      int n0, x0, y0, b;
-      decode(item, n0, x0, y0, b);
+      int n0, ph, x0, y0, b;
+      decode(item, n0, ph, x0, y0, b);
+      const TapList& tl = c_taps[UP ? 1 + ph : 0];
       for (int kc = 0; kc < p.n_kchunks; ++kc) {
         const int c0 = kc * KC;
         mbar_wait(a_empty + 8 * ia, pa ^ 1);
@@ -127,12 +136,12 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (p.nprod > 1) tma_load_4d(dst + p.a_plane, &tm_a_lo, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
         if (++ia == p.SA) { ia = 0; pa ^= 1; }
 #pragma unroll 1
-        for (int t = 0; t < 9; ++t) {
+        for (int t = 0; t < tl.n; ++t) {
           mbar_wait(b_empty + 8 * ib, pb ^ 1);
           mbar_expect_tx(b_full + 8 * ib, p.nprod > 1 ? b_stage : b_half);
           const uint32_t dstb = b_base + ib * b_stage;
-          tma_load_3d(dstb, &tm_b_hi, b_full + 8 * ib, c0, n0, taps[t].tap);
-          if (p.nprod > 1) tma_load_3d(dstb + b_half, &tm_b_lo, b_full + 8 * ib, c0, n0, taps[t].tap);
+          tma_load_3d(dstb, &tm_b_hi, b_full + 8 * ib, c0, n0, tl.t[t].tap);
+          if (p.nprod > 1) tma_load_3d(dstb + b_half, &tm_b_lo, b_full + 8 * ib, c0, n0, tl.t[t].tap);
           if (++ib == p.SB) { ib = 0; pb ^= 1; }
         }
       }
@@ -142,47 +151,57 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     // The issue loop must stay far below the ~50 cycles a 128x32x16 MMA occupies the tensor pipe: all descriptor
     // fields are folded into per-stage base values up front; per MMA only 64-bit adds of small constants remain.
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN);
+    const uint32_t idesc2 = make_idesc_bf16(128, (uint32_t)(2 * p.BN));
     const uint64_t sbo_field = (uint64_t)((((uint32_t)p.HW_ * ROW) >> 4) & 0x3FFF) << 32;
     const uint64_t da0 = (make_kmajor_desc(a_base, ROW) & ~(0x3FFFull << 32)) | sbo_field;  // A stage 0, hi plane
     const uint64_t db0 = make_kmajor_desc(b_base, ROW);                                      // B stage 0, hi plane
     const uint64_t a_stage16 = a_stage >> 4, a_plane16 = p.a_plane >> 4;
     const uint64_t b_stage16 = b_stage >> 4, b_half16 = b_half >> 4;
     const uint32_t rstep16 = (uint32_t)(TH * p.HW_) * ROW >> 4;  // next stacked tile: 16 halo rows further
-    const bool three = p.nprod > 1;
+    const int mode = p.nprod == 1 ? 0 : (p.cat ? 2 : 1);
     int ia = 0, ib = 0, as = 0;
     uint32_t pa = 0, pb = 0, pacc = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      int n0, ph, x0, y0, b;
+      decode(item, n0, ph, x0, y0, b);
+      const TapList& tl = c_taps[UP ? 1 + ph : 0];
       mbar_wait(acc_empty + 8 * as, pacc ^ 1);  // epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t acc_stage = tmem_base + (uint32_t)as * acc_cols;
-      uint32_t started = 0;
+      uint32_t first = 0;  // 0 for the very first MMA into each accumulator of the item
       for (int kc = 0; kc < p.n_kchunks; ++kc) {
         mbar_wait(a_full + 8 * ia, pa);
         const uint64_t da_stage = da0 + (uint64_t)ia * a_stage16;
 #pragma unroll 1
-        for (int t = 0; t < 9; ++t) {
-          const Tap tp = taps[t];
+        for (int t = 0; t < tl.n; ++t) {
+          const Tap tp = tl.t[t];
           mbar_wait(b_full + 8 * ib, pb);
           tc_fence_after();
           const uint64_t dbh = db0 + (uint64_t)ib * b_stage16, dbl = dbh + b_half16;
           uint64_t dah = da_stage + (uint64_t)((uint32_t)(tp.hy * p.HW_ + tp.hx) * ROW >> 4);
-          uint32_t acc = acc_stage + (uint32_t)(tp.phase * p.R) * (uint32_t)p.BN;
-          const uint32_t first = ((started >> tp.phase) & 1u);  // all R accumulators of a phase start together
+          uint32_t acc = acc_stage;
 #pragma unroll 1
           for (int r = 0; r < p.R; ++r) {
             const uint64_t dal = dah + a_plane16;
-            umma_bf16(acc, dah, dbh, idesc, first);
-            umma_bf16(acc, dah + 2, dbh + 2, idesc, 1u);
-            if (three) {
-              umma_bf16(acc, dah, dbl, idesc, 1u);
-              umma_bf16(acc, dah + 2, dbl + 2, idesc, 1u);
+            if (mode == 2) {  // [hi*hi | hi*lo] in one N = 2*BN MMA (B stage = hi rows followed by lo rows), then lo*hi
+              umma_bf16(acc, dah, dbh, idesc2, first);
+              umma_bf16(acc, dah + 2, dbh + 2, idesc2, 1u);
               umma_bf16(acc, dal, dbh, idesc, 1u);
               umma_bf16(acc, dal + 2, dbh + 2, idesc, 1u);
+            } else {
+              umma_bf16(acc, dah, dbh, idesc, first);
+              umma_bf16(acc, dah + 2, dbh + 2, idesc, 1u);
+              if (mode == 1) {
+                umma_bf16(acc, dah, dbl, idesc, 1u);
+                umma_bf16(acc, dah + 2, dbl + 2, idesc, 1u);
+                umma_bf16(acc, dal, dbh, idesc, 1u);
+                umma_bf16(acc, dal + 2, dbh + 2, idesc, 1u);
+              }
             }
             dah += rstep16;
-            acc += (uint32_t)p.BN;
+            acc += blk_cols;
           }
-          started |= 1u << tp.phase;
+          first = 1u;
           umma_commit(b_empty + 8 * ib);
           if (++ib == p.SB) { ib = 0; pb ^= 1; }
         }
@@ -204,19 +223,17 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     int as = 0;
     uint32_t pacc = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-    int n0, x0, y0, b;
-    decode(item, n0, x0, y0, b);
-    const int gx = x0 + tx;
-    mbar_wait(acc_full + 8 * as, pacc);
-    tc_fence_after();
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * acc_cols;
-    const float* dptr = ep.d ? ep.d + (long long)b * p.Cout + n0 : nullptr;
+      int n0, ph, x0, y0, b;
+      decode(item, n0, ph, x0, y0, b);
+      const int gx = x0 + tx;
+      mbar_wait(acc_full + 8 * as, pacc);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * acc_cols;
+      const float* dptr = ep.d ? ep.d + (long long)b * p.Cout + n0 : nullptr;
 #pragma unroll 1
-    for (int r = 0; r < p.R; ++r) {
-      const int gy = y0 + r * TH + ty;
-      const bool in_grid = (gy < p.GH) && (gx < p.GW);
-#pragma unroll 1
-      for (int ph = 0; ph < NPH; ++ph) {
+      for (int r = 0; r < p.R; ++r) {
+        const int gy = y0 + r * TH + ty;
+        const bool in_grid = (gy < p.GH) && (gx < p.GW);
         int oy, ox, OH, OW;
         bool valid;
         if (UP) {
@@ -230,13 +247,21 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         float nz = 0.f;
         if (!UP && ep.activate && ep.noise && valid)
           nz = nwv * __ldg(ep.noise + (long long)b * ep.noise_bstride + (long long)oy * OW + ox);
-        const uint32_t acc_col = (uint32_t)((ph * p.R + r) * p.BN);
+        const uint32_t acc_col = (uint32_t)r * blk_cols;
 #pragma unroll 1
         for (int c = 0; c < p.BN; c += 16) {
-          if ((((ph * p.R + r) * p.BN + c) >> 4) % EPI_GROUPS != egroup) continue;  // warp-uniform
+          if (((r * p.BN + c) >> 4) % EPI_GROUPS != egroup) continue;  // warp-uniform
           uint32_t rr[16];
           tmem_ld_x16(lane_addr + acc_col + (uint32_t)c, rr);
-          tmem_ld_wait();
+          if (p.cat) {
+            uint32_t r2[16];
+            tmem_ld_x16(lane_addr + acc_col + (uint32_t)(p.BN + c), r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
+          } else {
+            tmem_ld_wait();
+          }
           if (!valid) continue;
           float v[16];
           if (dptr) {
@@ -302,12 +327,11 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           }
         }
       }
-    }
       // accumulator stage drained: hand it back to the MMA issuer
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(acc_empty + 8 * as);
-    if (++as == p.AS) { as = 0; pacc ^= 1; }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+      if (++as == p.AS) { as = 0; pacc ^= 1; }
     }
   }
 
@@ -332,7 +356,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   if (GH < 4 * TH || GW < 4 * TW) return MAUA_E_UNSUPPORTED;  // <= 32^2: v1's batch-folded tiles fill the SMs better
   Params p;
   p.B = batch; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout; p.GH = GH; p.GW = GW;
-  const int nphase = up ? 4 : 1;
+  const int nphase = up ? 4 : 1;  // phases are separate work items: they do not multiply the accumulator columns
   const int kc = 32;  // 64-byte operand rows: the halo of R = 4 stacked tiles still fits next to a deep B ring
   const int n_kchunks = cin / kc;
   const long long tiles_x = ceil_div(GW, TW);
@@ -350,16 +374,20 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   for (int r = 4; r >= 1; r >>= 1) {
     if (r > rows16) continue;
     for (int bn = 256; bn >= 16; bn >>= 1) {
-      if (cout % bn != 0 || r * nphase * bn > tmem_cap) continue;
+      const int blk = (n_products > 1 && bn <= 64) ? 2 * bn : bn;  // concat mode doubles the accumulator width
+      if (cout % bn != 0 || r * blk > tmem_cap) continue;
       const uint32_t plane = align1k((uint32_t)((TH * r + (up ? 1 : 2)) * (up ? TW + 1 : TW + 2) * kc * 2));
       const uint32_t b_st = 2u * bn * kc * 2u;
       if (2 * plane + 4 * b_st > budget) continue;  // A halo (hi+lo) + a B ring deep enough to hide TMA latency
-      const long long ctas = tiles_x * ceil_div(rows16, (long long)r) * batch * (cout / bn);
+      const long long ctas = tiles_x * ceil_div(rows16, (long long)r) * batch * (cout / bn) * nphase;
       // modelled tensor-pipe cycles per MMA of N columns: max(math N/2, operand fetch (4 KB A + 32N B) / 128 B/clk);
       // single accumulator stage => the epilogue is exposed (penalty); L2->SMEM bytes per cycle as a tie-breaker
-      const double mma_cyc = (bn / 2.0 > 32.0 + bn / 4.0 ? bn / 2.0 : 32.0 + bn / 4.0) / bn;
+      // (the issue thread needs ~40 cycles per MMA, which also floors the small-N case)
+      auto mma_cycles = [](double n) { double c = n / 2.0; if (32.0 + n / 4.0 > c) c = 32.0 + n / 4.0; if (c < 40.0) c = 40.0; return c; };
+      const double per_kstep = (blk != bn) ? mma_cycles(2.0 * bn) + mma_cycles(bn) : (n_products > 1 ? 3.0 : 1.0) * mma_cycles(bn);
+      const double mma_cyc = per_kstep / bn;
       const double traffic = ((TH * r + 2) * 10.0 / 9.0 + bn) / ((double)r * bn);
-      double cost = mma_cyc * (2 * r * nphase * bn <= 512 ? 1.0 : 1.35) + 0.05 * traffic;
+      double cost = mma_cyc * (2 * r * blk <= 512 ? 1.0 : 1.35) + 0.15 * traffic;
       const bool enough = ctas >= 2 * 148, best_enough = best_ctas >= 2 * 148;
       const bool better = best_r == 0 || (enough && !best_enough) || (enough == best_enough && (enough ? cost < best_cost : ctas > best_ctas));
       if (better) { best_r = r; best_bn = bn; best_cost = cost; best_ctas = ctas; }
@@ -377,9 +405,10 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   p.n_kchunks = n_kchunks;
   p.nprod = n_products;
   p.a_plane = align1k((uint32_t)(p.HW_ * p.HH_ * kc * 2));
+  p.cat = (n_products > 1 && bn <= 64) ? 1 : 0;
+  const int blk_cols = p.cat ? 2 * bn : bn;
+  p.n_phase = nphase;
   int cols = 32;
-  while (cols < bn * nphase * R) cols <<= 1;
-  p.tmem_cols = (uint32_t)cols;
   const uint32_t a_stage = 2 * p.a_plane, b_stage = 2u * bn * kc * 2u;
   p.SA = (2 * a_stage + 4 * b_stage <= budget) ? 2 : 1;
   int sb = (int)((budget - (uint32_t)p.SA * a_stage) / b_stage);
@@ -388,12 +417,12 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   p.SB = sb;
   const size_t smem = (size_t)p.SA * a_stage + (size_t)p.SB * b_stage + 8 * (2 * p.SA + 2 * p.SB + 6) + 1024;
   if (smem > 227 * 1024) return MAUA_E_UNSUPPORTED;
-  const long long items = tiles_x * p.tiles_y * batch * p.n_tiles;
+  const long long items = tiles_x * p.tiles_y * batch * p.n_tiles * nphase;
   if (items >= (1LL << 31)) return MAUA_E_UNSUPPORTED;
   p.n_items = (int)items;
-  p.AS = (2 * bn * nphase * R <= 512) ? 2 : 1;
+  p.AS = (2 * blk_cols * R <= 512) ? 2 : 1;
   cols = 32;
-  while (cols < p.AS * bn * nphase * R) cols <<= 1;
+  while (cols < p.AS * blk_cols * R) cols <<= 1;
   p.tmem_cols = (uint32_t)cols;
   static int n_sm = 0;
   if (n_sm == 0) {
@@ -404,8 +433,8 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   const long long grid = items < n_sm ? items : n_sm;
   static const bool debug = [] { const char* e = getenv("MAUA_TC_DEBUG"); return e && e[0] == '1'; }();
   if (debug)
-    fprintf(stderr, "[modconv_tc2] %s B%d %d->%d @%dx%d: R=%d BN=%d AS=%d SA=%d SB=%d smem=%zuKB tmem=%u items=%lld grid=%lld\n",
-            up ? "up" : "same", batch, cin, cout, h, w, R, bn, p.AS, p.SA, p.SB, smem / 1024, p.tmem_cols, items, grid);
+    fprintf(stderr, "[modconv_tc2] %s B%d %d->%d @%dx%d: R=%d BN=%d cat=%d AS=%d SA=%d SB=%d smem=%zuKB tmem=%u items=%lld grid=%lld\n",
+            up ? "up" : "same", batch, cin, cout, h, w, R, bn, p.cat, p.AS, p.SA, p.SB, smem / 1024, p.tmem_cols, items, grid);
 
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   const auto swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
