@@ -42,21 +42,18 @@ struct Params {
   uint32_t a_plane;      // bytes of one bf16 plane of the halo, rounded up to 1024
   uint32_t tmem_cols;
   int AS;                // TMEM accumulator stages (2 = epilogue of item i overlaps the MMAs of item i+1)
-  int n_phase;           // 1 same-res, 4 transposed (each sub-pixel phase is its own work item)
-  int n_items;           // work items = n_tiles * n_phase * tiles_x * tiles_y * B, walked with stride gridDim.x
+  int n_phase;           // accumulator phases per item: 1 same-res, 4 transposed
+  int n_items;           // work items = n_tiles * tiles_x * tiles_y * B, walked with stride gridDim.x
 };
 
-// Tap lists.  same-res: tap (ky,kx) reads x[y+ky-1, x+kx-1] -> halo (ky, kx).
+// Tap lists.  same-res: tap (ky,kx) reads x[y+ky-1, x+kx-1] -> halo (ky, kx), one accumulator phase.
 // transposed: u[2y'+py, 2x'+px] += W[ky,kx] * x[y'+dy, x'+dx], py = ky&1, dy = (ky==2 ? -1 : 0) -> halo row dy+1;
-// phase (py,px) owns the taps with ky&1 == py and kx&1 == px: 4 / 2 / 2 / 1 taps.
-struct Tap { int8_t hy, hx, tap, pad; };
+// the four sub-pixel phases (py,px) accumulate side by side in TMEM and share the one halo load.
+struct Tap { int8_t hy, hx, tap, phase; };
 struct TapList { int32_t n; Tap t[9]; };
-__constant__ TapList c_taps[5] = {
+__constant__ TapList c_taps[2] = {
     {9, {{0, 0, 0, 0}, {0, 1, 1, 0}, {0, 2, 2, 0}, {1, 0, 3, 0}, {1, 1, 4, 0}, {1, 2, 5, 0}, {2, 0, 6, 0}, {2, 1, 7, 0}, {2, 2, 8, 0}}},
-    {4, {{1, 1, 0, 0}, {1, 0, 2, 0}, {0, 1, 6, 0}, {0, 0, 8, 0}}},  // phase 0: (0,0) (0,2) (2,0) (2,2)
-    {2, {{1, 1, 1, 0}, {0, 1, 7, 0}}},                              // phase 1: (0,1) (2,1)
-    {2, {{1, 1, 3, 0}, {1, 0, 5, 0}}},                              // phase 2: (1,0) (1,2)
-    {1, {{1, 1, 4, 0}}}};                                           // phase 3: (1,1)
+    {9, {{1, 1, 0, 0}, {1, 1, 1, 1}, {1, 0, 2, 0}, {1, 1, 3, 2}, {1, 1, 4, 3}, {1, 0, 5, 2}, {0, 1, 6, 0}, {0, 1, 7, 1}, {0, 0, 8, 0}}}};
 
 __device__ __forceinline__ float lrelu_s(float v, float slope, float scale) { return (v > 0.f ? v : v * slope) * scale; }
 
@@ -103,20 +100,19 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // work item -> (n tile, phase, pixel tile); n fastest, then phase: concurrently running CTAs share the activation
-  // halo through L2
-  auto decode = [&](int item, int& n0, int& ph, int& x0, int& y0, int& b) {
+  // work item -> (n tile, pixel tile); n fastest: concurrently running CTAs share the activation halo through L2
+  auto decode = [&](int item, int& n0, int& x0, int& y0, int& b) {
     const int n_tile = item % p.n_tiles;
-    int rest = item / p.n_tiles;
-    ph = rest % p.n_phase;
-    rest /= p.n_phase;
+    const int rest = item / p.n_tiles;
     x0 = (rest % p.tiles_x) * TW;
     y0 = ((rest / p.tiles_x) % p.tiles_y) * TH * p.R;
     b = rest / (p.tiles_x * p.tiles_y);
     n0 = n_tile * p.BN;
   };
+  constexpr int NPH = UP ? 4 : 1;
+  const TapList& tl = c_taps[UP ? 1 : 0];
   const uint32_t blk_cols = (uint32_t)(p.cat ? 2 * p.BN : p.BN);  // TMEM columns of one accumulator
-  const uint32_t acc_cols = (uint32_t)p.R * blk_cols;             // ... of one accumulator stage
+  const uint32_t acc_cols = (uint32_t)(NPH * p.R) * blk_cols;     // ... of one accumulator stage
   const uint32_t halo_bytes = (uint32_t)(p.HW_ * p.HH_) * ROW;    // bytes one TMA box writes per plane
 
   if (warp == 0 && lane == 0) {
@@ -124,9 +120,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      int n0, ph, x0, y0, b;
-      decode(item, n0, ph, x0, y0, b);
-      const TapList& tl = c_taps[UP ? 1 + ph : 0];
+      int n0, x0, y0, b;
+      decode(item, n0, x0, y0, b);
       for (int kc = 0; kc < p.n_kchunks; ++kc) {
         const int c0 = kc * KC;
         mbar_wait(a_empty + 8 * ia, pa ^ 1);
@@ -162,13 +157,12 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     int ia = 0, ib = 0, as = 0;
     uint32_t pa = 0, pb = 0, pacc = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      int n0, ph, x0, y0, b;
-      decode(item, n0, ph, x0, y0, b);
-      const TapList& tl = c_taps[UP ? 1 + ph : 0];
+      int n0, x0, y0, b;
+      decode(item, n0, x0, y0, b);
       mbar_wait(acc_empty + 8 * as, pacc ^ 1);  // epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t acc_stage = tmem_base + (uint32_t)as * acc_cols;
-      uint32_t first = 0;  // 0 for the very first MMA into each accumulator of the item
+      uint32_t started = 0;  // bit ph: the accumulators of phase ph have received their first MMA
       for (int kc = 0; kc < p.n_kchunks; ++kc) {
         mbar_wait(a_full + 8 * ia, pa);
         const uint64_t da_stage = da0 + (uint64_t)ia * a_stage16;
@@ -179,7 +173,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           tc_fence_after();
           const uint64_t dbh = db0 + (uint64_t)ib * b_stage16, dbl = dbh + b_half16;
           uint64_t dah = da_stage + (uint64_t)((uint32_t)(tp.hy * p.HW_ + tp.hx) * ROW >> 4);
-          uint32_t acc = acc_stage;
+          uint32_t acc = acc_stage + (uint32_t)(tp.phase * p.R) * blk_cols;
+          const uint32_t first = (started >> tp.phase) & 1u;
 #pragma unroll 1
           for (int r = 0; r < p.R; ++r) {
             const uint64_t dal = dah + a_plane16;
@@ -201,7 +196,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             dah += rstep16;
             acc += blk_cols;
           }
-          first = 1u;
+          started |= 1u << tp.phase;
           umma_commit(b_empty + 8 * ib);
           if (++ib == p.SB) { ib = 0; pb ^= 1; }
         }
@@ -223,8 +218,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     int as = 0;
     uint32_t pacc = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      int n0, ph, x0, y0, b;
-      decode(item, n0, ph, x0, y0, b);
+      int n0, x0, y0, b;
+      decode(item, n0, x0, y0, b);
       const int gx = x0 + tx;
       mbar_wait(acc_full + 8 * as, pacc);
       tc_fence_after();
@@ -234,6 +229,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       for (int r = 0; r < p.R; ++r) {
         const int gy = y0 + r * TH + ty;
         const bool in_grid = (gy < p.GH) && (gx < p.GW);
+#pragma unroll 1
+        for (int ph = 0; ph < NPH; ++ph) {
         int oy, ox, OH, OW;
         bool valid;
         if (UP) {
@@ -247,10 +244,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         float nz = 0.f;
         if (!UP && ep.activate && ep.noise && valid)
           nz = nwv * __ldg(ep.noise + (long long)b * ep.noise_bstride + (long long)oy * OW + ox);
-        const uint32_t acc_col = (uint32_t)r * blk_cols;
+        const uint32_t acc_col = (uint32_t)(ph * p.R + r) * blk_cols;
 #pragma unroll 1
         for (int c = 0; c < p.BN; c += 16) {
-          if (((r * p.BN + c) >> 4) % EPI_GROUPS != egroup) continue;  // warp-uniform
+          if ((((ph * p.R + r) * p.BN + c) >> 4) % EPI_GROUPS != egroup) continue;  // warp-uniform
           uint32_t rr[16];
           tmem_ld_x16(lane_addr + acc_col + (uint32_t)c, rr);
           if (p.cat) {
@@ -326,6 +323,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             }
           }
         }
+        }
       }
       // accumulator stage drained: hand it back to the MMA issuer
       tc_fence_before();
@@ -356,7 +354,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   if (GH < 4 * TH || GW < 4 * TW) return MAUA_E_UNSUPPORTED;  // <= 32^2: v1's batch-folded tiles fill the SMs better
   Params p;
   p.B = batch; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout; p.GH = GH; p.GW = GW;
-  const int nphase = up ? 4 : 1;  // phases are separate work items: they do not multiply the accumulator columns
+  const int nphase = up ? 4 : 1;
   const int kc = 32;  // 64-byte operand rows: the halo of R = 4 stacked tiles still fits next to a deep B ring
   const int n_kchunks = cin / kc;
   const long long tiles_x = ceil_div(GW, TW);
@@ -368,29 +366,32 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   // Pick (R, BN): minimise L2->SMEM bytes per tensor-pipe cycle,
   //   bytes/cycle ~ [ (16R+2)*10/9 + BN ] / (R*BN)      (A halo amortised over 9 taps + one B tile per tap)
   // subject to TMEM columns, shared memory (A halo + >= 2 B stages) and a grid that covers the 148 SMs.
-  int best_r = 0, best_bn = 0;
+  int best_r = 0, best_bn = 0, best_cat = 0;
   double best_cost = 1e30;
   long long best_ctas = 0;
   for (int r = 4; r >= 1; r >>= 1) {
     if (r > rows16) continue;
     for (int bn = 256; bn >= 16; bn >>= 1) {
-      const int blk = (n_products > 1 && bn <= 64) ? 2 * bn : bn;  // concat mode doubles the accumulator width
-      if (cout % bn != 0 || r * blk > tmem_cap) continue;
-      const uint32_t plane = align1k((uint32_t)((TH * r + (up ? 1 : 2)) * (up ? TW + 1 : TW + 2) * kc * 2));
-      const uint32_t b_st = 2u * bn * kc * 2u;
-      if (2 * plane + 4 * b_st > budget) continue;  // A halo (hi+lo) + a B ring deep enough to hide TMA latency
-      const long long ctas = tiles_x * ceil_div(rows16, (long long)r) * batch * (cout / bn) * nphase;
-      // modelled tensor-pipe cycles per MMA of N columns: max(math N/2, operand fetch (4 KB A + 32N B) / 128 B/clk);
-      // single accumulator stage => the epilogue is exposed (penalty); L2->SMEM bytes per cycle as a tie-breaker
-      // (the issue thread needs ~40 cycles per MMA, which also floors the small-N case)
-      auto mma_cycles = [](double n) { double c = n / 2.0; if (32.0 + n / 4.0 > c) c = 32.0 + n / 4.0; if (c < 40.0) c = 40.0; return c; };
-      const double per_kstep = (blk != bn) ? mma_cycles(2.0 * bn) + mma_cycles(bn) : (n_products > 1 ? 3.0 : 1.0) * mma_cycles(bn);
-      const double mma_cyc = per_kstep / bn;
-      const double traffic = ((TH * r + 2) * 10.0 / 9.0 + bn) / ((double)r * bn);
-      double cost = mma_cyc * (2 * r * blk <= 512 ? 1.0 : 1.35) + 0.15 * traffic;
-      const bool enough = ctas >= 2 * 148, best_enough = best_ctas >= 2 * 148;
-      const bool better = best_r == 0 || (enough && !best_enough) || (enough == best_enough && (enough ? cost < best_cost : ctas > best_ctas));
-      if (better) { best_r = r; best_bn = bn; best_cost = cost; best_ctas = ctas; }
+      if (cout % bn != 0) continue;
+      for (int cat = 0; cat <= ((n_products > 1 && bn <= 64) ? 1 : 0); ++cat) {
+        const int blk = cat ? 2 * bn : bn;  // concat mode doubles the accumulator width
+        if (r * blk * nphase > tmem_cap) continue;
+        const uint32_t plane = align1k((uint32_t)((TH * r + (up ? 1 : 2)) * (up ? TW + 1 : TW + 2) * kc * 2));
+        const uint32_t b_st = 2u * bn * kc * 2u;
+        if (2 * plane + 4 * b_st > budget) continue;  // A halo (hi+lo) + a B ring deep enough to hide TMA latency
+        const long long ctas = tiles_x * ceil_div(rows16, (long long)r) * batch * (cout / bn);
+        // modelled tensor-pipe cycles per MMA of N columns: max(math N/2, operand fetch (4 KB A + 32N B) / 128 B/clk,
+        // ~40 cycles of issue overhead); a single accumulator stage exposes the epilogue (penalty); L2->SMEM bytes
+        // per cycle [ (16R+2)*10/9 + BN ] / (R*BN) as a secondary term
+        auto mma_cycles = [](double n) { double c = n / 2.0; if (32.0 + n / 4.0 > c) c = 32.0 + n / 4.0; if (c < 40.0) c = 40.0; return c; };
+        const double per_kstep = cat ? mma_cycles(2.0 * bn) + mma_cycles(bn) : (n_products > 1 ? 3.0 : 1.0) * mma_cycles(bn);
+        const double traffic = ((TH * r + 2) * 10.0 / 9.0 + bn) / ((double)r * bn);
+        const double cost = per_kstep / bn * (2 * r * blk * nphase <= 512 ? 1.0 : 1.35) + 0.15 * traffic;
+        const bool enough = ctas >= 2 * 148, best_enough = best_ctas >= 2 * 148;
+        const bool better = best_r == 0 || (enough && !best_enough) ||
+                            (enough == best_enough && (enough ? cost < best_cost : ctas > best_ctas));
+        if (better) { best_r = r; best_bn = bn; best_cat = cat; best_cost = cost; best_ctas = ctas; }
+      }
     }
   }
   if (best_r == 0) return MAUA_E_UNSUPPORTED;
@@ -405,7 +406,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   p.n_kchunks = n_kchunks;
   p.nprod = n_products;
   p.a_plane = align1k((uint32_t)(p.HW_ * p.HH_ * kc * 2));
-  p.cat = (n_products > 1 && bn <= 64) ? 1 : 0;
+  p.cat = best_cat;
   const int blk_cols = p.cat ? 2 * bn : bn;
   p.n_phase = nphase;
   int cols = 32;
@@ -417,12 +418,12 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   p.SB = sb;
   const size_t smem = (size_t)p.SA * a_stage + (size_t)p.SB * b_stage + 8 * (2 * p.SA + 2 * p.SB + 6) + 1024;
   if (smem > 227 * 1024) return MAUA_E_UNSUPPORTED;
-  const long long items = tiles_x * p.tiles_y * batch * p.n_tiles * nphase;
+  const long long items = tiles_x * p.tiles_y * batch * p.n_tiles;
   if (items >= (1LL << 31)) return MAUA_E_UNSUPPORTED;
   p.n_items = (int)items;
-  p.AS = (2 * blk_cols * R <= 512) ? 2 : 1;
+  p.AS = (2 * blk_cols * R * nphase <= 512) ? 2 : 1;
   cols = 32;
-  while (cols < p.AS * blk_cols * R) cols <<= 1;
+  while (cols < p.AS * blk_cols * R * nphase) cols <<= 1;
   p.tmem_cols = (uint32_t)cols;
   static int n_sm = 0;
   if (n_sm == 0) {
