@@ -348,7 +348,7 @@ def main():
         if rank == 0:
             names = {"maua_modconv_tc", "maua_modconv_simt_f32", "maua_blur_act_nhwc", "maua_torgb_f32",
                      "maua_modulate_split_nhwc", "maua_style_prologue_f32", "maua_rgb_to_u8_nhwc", "maua_upfirdn2d_f32",
-                     "maua_noise_bias_act_f32"}
+                     "maua_noise_bias_act_f32", "maua_rgb_finish_f32", "maua_rgb_weights_f32"}
             L.PROFILE = {"names": names, "events": []}
             nprof = 3
             for i in range(nprof):

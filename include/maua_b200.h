@@ -122,6 +122,13 @@ int maua_noise_bias_act_f32(const float* x, const float* noise, const float* noi
 int maua_torgb_f32(const float* x, const float* wrgb, const float* s, const float* bias, const float* skip,
                    const float* k4, float* y, int batch, int cin, int h, int w, float w_scale, void* stream);
 
+/* wr[b,k,c] = w_scale * wrgb[k,c] * s[b,c]   (per-sample ToRGB rows for the fused conv epilogue) */
+int maua_rgb_weights_f32(const float* wrgb, const float* s, float* wr, int batch, int cin, float w_scale, void* stream);
+
+/* y[b,k] = (partial[b,k] + bias[k]) + upfirdn2d(skip, k4, up=2, pad=(2,1))[b,k]   (ToRGB tail after a fused epilogue) */
+int maua_rgb_finish_f32(const float* partial, const float* bias, const float* skip, const float* k4, float* y,
+                        int batch, int h, int w, void* stream);
+
 /* out[b,y,x,c] = (uint8) trunc( (clamp(rgb[b,c,y,x], -1, 1) + 1) * 127.5 ) */
 int maua_rgb_to_u8_nhwc(const float* rgb, uint8_t* out, int batch, int h, int w, void* stream);
 
@@ -158,6 +165,10 @@ typedef struct MauaConvEpilogue {
   float act_scale;           /* sqrt(2)                                                                   */
   int32_t activate;          /* 0: linear (no noise/bias/act), 1: noise+bias+lrelu                        */
   int32_t reserved;
+  /* Optional fused ToRGB partial sums (same-resolution layers whose whole Cout fits one N tile, Cout <= 128):
+   * rgb_out[b,k,y,x] = sum_c rgb_w[b,k,c] * act[b,c,y,x]  (no bias / skip: see maua_rgb_finish_f32).            */
+  const float* rgb_w;        /* [B,3,Cout] = w_scale * Wrgb[k,c] * s_rgb[b,c] (maua_rgb_weights_f32) or NULL     */
+  float* rgb_out;            /* [B,3,H,W] fp32                                                                    */
 } MauaConvEpilogue;
 
 /* 3x3 modulated conv on the tensor cores.  x_hi/x_lo [B,H,W,Cin] bf16 (pre-scaled by s), w_hi/w_lo [9][Cout][Cin].

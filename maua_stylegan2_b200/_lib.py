@@ -25,7 +25,8 @@ class ConvEpilogue(C.Structure):
     _fields_ = [("d", C.c_void_p), ("noise", C.c_void_p), ("noise_weight", C.c_void_p), ("bias", C.c_void_p),
                 ("s_next", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_f32_nchw", C.c_void_p),
                 ("out_raw_nhwc", C.c_void_p), ("noise_bstride", C.c_longlong), ("slope", C.c_float),
-                ("act_scale", C.c_float), ("activate", C.c_int32), ("reserved", C.c_int32)]
+                ("act_scale", C.c_float), ("activate", C.c_int32), ("reserved", C.c_int32), ("rgb_w", C.c_void_p),
+                ("rgb_out", C.c_void_p)]
 
 
 _p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
@@ -41,6 +42,8 @@ SIGNATURES = {
     "maua_noise_bias_act_f32": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _ll, _f, _f, _p],
     "maua_torgb_f32": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p],
     "maua_rgb_to_u8_nhwc": [_p, _p, _i, _i, _i, _p],
+    "maua_rgb_weights_f32": [_p, _p, _p, _i, _i, _f, _p],
+    "maua_rgb_finish_f32": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "maua_pack_weight_bf16x2": [_p, _p, _p, _i, _i, _i, _f, _p],
     "maua_modulate_split_nhwc": [_p, _ll, _p, _p, _p, _i, _i, _i, _i, _p],
     "maua_modconv_tc": [_p, _p, _p, _p, C.POINTER(ConvEpilogue), _i, _i, _i, _i, _i, _i, _i, _p],

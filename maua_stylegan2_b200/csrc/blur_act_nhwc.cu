@@ -190,6 +190,25 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_tma_kernel(const __grid_
   int it = 0;
   for (int t = first; t < n_tiles; t += step, ++it) {
     const int stage = it & 1;
+    // tile coordinates and epilogue operands first: these global loads overlap the TMA wait and the FMA phase
+    int cg, ox0, oy0, b;
+    decode(t, cg, ox0, oy0, b);
+    const int cbase = cg * BCH + c4 * 4;
+    const int ox = ox0 + lx;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), sn = make_float4(1.f, 1.f, 1.f, 1.f);
+    float nzv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) nzv[j] = 0.f;
+    if (ox < ow) {
+      if (ep.activate && ep.bias) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + cbase));
+      if (ep.s_next) sn = __ldg(reinterpret_cast<const float4*>(ep.s_next + (long long)b * ch + cbase));
+      if (ep.activate && ep.noise) {
+        const float* np = ep.noise + (long long)b * ep.noise_bstride + (long long)(oy0 + ly0) * ow + ox;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (oy0 + ly0 + j < oh) nzv[j] = __ldg(np + (long long)j * ow);
+      }
+    }
     mbar_wait(bar0 + 8 * stage, (it >> 1) & 1);
     const float* tile = tile_ptr[stage];
     float4 acc[8];
@@ -221,22 +240,14 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_tma_kernel(const __grid_
       issue(t + 2 * step, stage);
     }
 
-    int cg, ox0, oy0, b;
-    decode(t, cg, ox0, oy0, b);
-    const int cbase = cg * BCH + c4 * 4;
-    const int ox = ox0 + lx;
     if (ox >= ow) continue;
-    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), sn = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (ep.activate && ep.bias) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + cbase));
-    if (ep.s_next) sn = __ldg(reinterpret_cast<const float4*>(ep.s_next + (long long)b * ch + cbase));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int oy = oy0 + ly0 + j;
       if (oy >= oh) break;
       float v0 = acc[j].x, v1 = acc[j].y, v2 = acc[j].z, v3 = acc[j].w;
       if (ep.activate) {
-        float nz = 0.f;
-        if (ep.noise) nz = __fmul_rn(nw, __ldg(ep.noise + (long long)b * ep.noise_bstride + (long long)oy * ow + ox));
+        const float nz = __fmul_rn(nw, nzv[j]);
         v0 = lrelu_scaled(__fadd_rn(__fadd_rn(v0, nz), bias.x), ep.slope, ep.act_scale);
         v1 = lrelu_scaled(__fadd_rn(__fadd_rn(v1, nz), bias.y), ep.slope, ep.act_scale);
         v2 = lrelu_scaled(__fadd_rn(__fadd_rn(v2, nz), bias.z), ep.slope, ep.act_scale);

@@ -314,7 +314,8 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
   if (up) {
     MAUA_CHECK_ARG(ep.out_raw_nhwc, "modconv_tc(up): out_raw_nhwc required");
   } else {
-    MAUA_CHECK_ARG(ep.out_f32_nchw || ep.out_hi, "modconv_tc: no output requested");
+    MAUA_CHECK_ARG(ep.out_f32_nchw || ep.out_hi || ep.rgb_out, "modconv_tc: no output requested");
+    MAUA_CHECK_ARG((ep.rgb_out != nullptr) == (ep.rgb_w != nullptr), "modconv_tc: rgb_w / rgb_out must come in pairs");
     MAUA_CHECK_ARG((ep.out_hi != nullptr) == (ep.out_lo != nullptr), "modconv_tc: hi/lo outputs must come in pairs");
     MAUA_CHECK_ARG(!ep.noise || ep.noise_weight, "modconv_tc: noise without noise_weight");
   }
@@ -328,6 +329,7 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
     if (rc2 != MAUA_E_UNSUPPORTED) return rc2;
   }
 
+  MAUA_CHECK_ARG(!ep.rgb_out, "modconv_tc: fused ToRGB is not available for this shape (needs Cout <= 128, H,W >= 64)");
   Params p;
   p.B = batch; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout;
   p.GH = up ? h + 1 : h;

@@ -225,8 +225,13 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * acc_cols;
       const float* dptr = ep.d ? ep.d + (long long)b * p.Cout + n0 : nullptr;
+      // fused ToRGB (host guarantees BN == Cout): one warp owns all chunks of a tile so that the three dot products
+      // are summed in a fixed (ascending channel) order
+      const bool fuse_rgb = !UP && ep.rgb_out != nullptr;
+      const float* wr = fuse_rgb ? ep.rgb_w + (long long)b * 3 * p.Cout : nullptr;
 #pragma unroll 1
       for (int r = 0; r < p.R; ++r) {
+        float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
         const int gy = y0 + r * TH + ty;
         const bool in_grid = (gy < p.GH) && (gx < p.GW);
 #pragma unroll 1
@@ -247,7 +252,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const uint32_t acc_col = (uint32_t)(ph * p.R + r) * blk_cols;
 #pragma unroll 1
         for (int c = 0; c < p.BN; c += 16) {
-          if ((((ph * p.R + r) * p.BN + c) >> 4) % EPI_GROUPS != egroup) continue;  // warp-uniform
+          if ((fuse_rgb ? r : (((ph * p.R + r) * p.BN + c) >> 4)) % EPI_GROUPS != egroup) continue;  // warp-uniform
           uint32_t rr[16];
           tmem_ld_x16(lane_addr + acc_col + (uint32_t)c, rr);
           if (p.cat) {
@@ -290,6 +295,20 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 v[4 * q + 3] = lrelu_s((v[4 * q + 3] + nz) + bv.w, ep.slope, ep.act_scale);
               }
             }
+            if (fuse_rgb) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr + c) + q);
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr + p.Cout + c) + q);
+                const float4 w2 = __ldg(reinterpret_cast<const float4*>(wr + 2 * p.Cout + c) + q);
+                rgb0 = fmaf(v[4 * q], w0.x, rgb0); rgb0 = fmaf(v[4 * q + 1], w0.y, rgb0);
+                rgb0 = fmaf(v[4 * q + 2], w0.z, rgb0); rgb0 = fmaf(v[4 * q + 3], w0.w, rgb0);
+                rgb1 = fmaf(v[4 * q], w1.x, rgb1); rgb1 = fmaf(v[4 * q + 1], w1.y, rgb1);
+                rgb1 = fmaf(v[4 * q + 2], w1.z, rgb1); rgb1 = fmaf(v[4 * q + 3], w1.w, rgb1);
+                rgb2 = fmaf(v[4 * q], w2.x, rgb2); rgb2 = fmaf(v[4 * q + 1], w2.y, rgb2);
+                rgb2 = fmaf(v[4 * q + 2], w2.z, rgb2); rgb2 = fmaf(v[4 * q + 3], w2.w, rgb2);
+              }
+            }
             if (ep.out_f32_nchw) {
               float* dst = ep.out_f32_nchw + (((long long)b * p.Cout + n0 + c) * OH + oy) * OW + ox;
               const long long plane = (long long)OH * OW;
@@ -323,6 +342,14 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             }
           }
         }
+        }
+        if (fuse_rgb && (r % EPI_GROUPS == egroup)) {
+          const int gy2 = y0 + r * TH + ty;
+          if (gy2 < p.H && gx < p.W) {
+            float* o = ep.rgb_out + (((long long)b * 3) * p.H + gy2) * p.W + gx;
+            const long long plane = (long long)p.H * p.W;
+            o[0] = rgb0; o[plane] = rgb1; o[2 * plane] = rgb2;
+          }
         }
       }
       // accumulator stage drained: hand it back to the MMA issuer
@@ -373,6 +400,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     if (r > rows16) continue;
     for (int bn = 256; bn >= 16; bn >>= 1) {
       if (cout % bn != 0) continue;
+      if (ep.rgb_out && bn != cout) continue;  // fused ToRGB needs every output channel in one CTA
       for (int cat = 0; cat <= ((n_products > 1 && bn <= 64) ? 1 : 0); ++cat) {
         const int blk = cat ? 2 * bn : bn;  // concat mode doubles the accumulator width
         if (r * blk * nphase > tmem_cap) continue;

@@ -144,6 +144,36 @@ __global__ void __launch_bounds__(256) torgb_small_kernel(const float* __restric
   }
 }
 
+__global__ void __launch_bounds__(256) rgb_weights_kernel(const float* __restrict__ wrgb, const float* __restrict__ s,
+                                                          float* __restrict__ wr, int cin, float w_scale, int total) {
+  const int i = blockIdx.x * 256 + threadIdx.x;  // over [B][3][cin]
+  if (i >= total) return;
+  const int c = i % cin, k = (i / cin) % 3, b = i / (3 * cin);
+  float v = __ldg(wrgb + k * cin + c) * w_scale;
+  if (s) v *= __ldg(s + (long long)b * cin + c);
+  wr[i] = v;
+}
+
+__global__ void __launch_bounds__(256) rgb_finish_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
+                                                         const float* __restrict__ skip, const float* __restrict__ k4,
+                                                         float* __restrict__ y, int h, int w, long long total) {
+  __shared__ float kf[16];
+  if (threadIdx.x < 16) kf[threadIdx.x] = k4 ? __ldg(k4 + threadIdx.x) : 0.f;
+  __syncthreads();
+  const long long hw = (long long)h * w;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long plane = i / hw;  // b*3 + k
+    const int pidx = (int)(i - plane * hw);
+    const int k = (int)(plane % 3);
+    float o = __fadd_rn(partial[i], bias ? __ldg(bias + k) : 0.f);
+    if (skip) {
+      const int oy = pidx / w, ox = pidx - oy * w;
+      o = __fadd_rn(o, skip_up2(skip + plane * (h >> 1) * (w >> 1), h >> 1, w >> 1, kf, oy, ox));
+    }
+    y[i] = o;
+  }
+}
+
 // one thread = one pixel (3 planar loads coalesced across the warp, 3 packed bytes out)
 __global__ void __launch_bounds__(256) rgb_to_u8_kernel(const float* __restrict__ rgb, uint8_t* __restrict__ out,
                                                         long long hw, long long total) {
@@ -199,5 +229,30 @@ extern "C" int maua_rgb_to_u8_nhwc(const float* rgb, uint8_t* out, int batch, in
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   rgb_to_u8_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(rgb, out, hw, total);
   MAUA_CHECK_LAUNCH("rgb_to_u8");
+  return MAUA_OK;
+}
+
+extern "C" int maua_rgb_weights_f32(const float* wrgb, const float* s, float* wr, int batch, int cin, float w_scale,
+                                    void* stream) {
+  using namespace maua;
+  MAUA_CHECK_ARG(wrgb && wr && batch >= 0 && cin >= 1, "rgb_weights: bad arguments");
+  const int total = batch * 3 * cin;
+  if (total == 0) return MAUA_OK;
+  rgb_weights_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(wrgb, s, wr, cin, w_scale, total);
+  MAUA_CHECK_LAUNCH("rgb_weights");
+  return MAUA_OK;
+}
+
+extern "C" int maua_rgb_finish_f32(const float* partial, const float* bias, const float* skip, const float* k4, float* y,
+                                   int batch, int h, int w, void* stream) {
+  using namespace maua;
+  MAUA_CHECK_ARG(partial && y && batch >= 0 && h >= 1 && w >= 1, "rgb_finish: bad arguments");
+  MAUA_CHECK_ARG(!skip || (k4 && (h % 2 == 0) && (w % 2 == 0)), "rgb_finish: skip needs k4 and even output size");
+  const long long total = (long long)batch * 3 * h * w;
+  if (total == 0) return MAUA_OK;
+  long long blocks = ceil_div(total, 256LL);
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  rgb_finish_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(partial, bias, skip, k4, y, h, w, total);
+  MAUA_CHECK_LAUNCH("rgb_finish");
   return MAUA_OK;
 }

@@ -8,6 +8,7 @@ and a torgb launch per resolution.  Python bends (`transform_dict_list`) are app
 between layers, exactly where the reference applies them (ManipulationLayer, models/stylegan2.py:297-307).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -15,6 +16,9 @@ from . import _lib as L
 from .plan import batch_buffers
 from .stylegan2 import SQRT2, _modconv_simt, _noise_bias_act, _prep_noise, _torgb, frames_to_u8
 from .op import upfirdn2d
+
+
+_FUSE_RGB = os.environ.get("MAUA_FUSE_RGB", "1") == "1"
 
 
 def _bend(x, layer_id, bends):
@@ -100,7 +104,12 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
                 if split is None:
                     split = _modulate_split(x.contiguous(), x_bstride, s, batch)
                 want_split = nxt is not None and nxt.tc_ok and not bend_here
-                want_f32 = want_acts or bend_here or sp.rgb is not None or (nxt is not None and not want_split)
+                # ToRGB fused into the conv epilogue when one CTA sees every output channel (Cout <= 128, halo kernel):
+                # the epilogue emits 3 partial sums per pixel instead of the Cout-channel fp32 map that torgb would re-read
+                fuse_rgb = (sp.rgb is not None and not sp.up and not want_acts and not bend_here and sp.cout <= 128
+                            and in_h >= 64 and in_w >= 32 and g.min_rgb_size <= out_h
+                            and _FUSE_RGB)
+                want_f32 = want_acts or bend_here or (sp.rgb is not None and not fuse_rgb) or (nxt is not None and not want_split)
                 y = torch.empty((batch, sp.cout, out_h, out_w), device=device, dtype=torch.float32) if want_f32 else None
                 o_hi = o_lo = None
                 if want_split:
@@ -114,6 +123,14 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
                 ep.out_hi, ep.out_lo = L.ptr(o_hi), L.ptr(o_lo)
                 ep.out_f32_nchw = L.ptr(y)
                 ep.slope, ep.act_scale, ep.activate = 0.2, SQRT2, 1
+                rgb_partial = None
+                if fuse_rgb:
+                    rs_f, _ = bc["views"][lp.rgb_job]
+                    wr = torch.empty((batch, 3, sp.cout), device=device, dtype=torch.float32)
+                    L.call("maua_rgb_weights_f32", sp.rgb.conv.weight.data_ptr(), rs_f.data_ptr(), wr.data_ptr(), batch,
+                           sp.cout, float(sp.rgb.conv.scale), stream)
+                    rgb_partial = torch.empty((batch, 3, out_h, out_w), device=device, dtype=torch.float32)
+                    ep.rgb_w, ep.rgb_out = wr.data_ptr(), rgb_partial.data_ptr()
                 if not sp.up:
                     ep.d = d.data_ptr()
                     L.call("maua_modconv_tc", split[0].data_ptr(), split[1].data_ptr(), lp.w_hi.data_ptr(),
@@ -145,7 +162,13 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
             if want_acts:
                 acts.append(x)
             current_size *= 2 if (sp.up or li == 0) else 1
-            if sp.rgb is not None:
+            if sp.rgb is not None and lp.tc_ok and rgb_partial is not None:
+                new_image = torch.empty_like(rgb_partial)
+                L.call("maua_rgb_finish_f32", rgb_partial.data_ptr(), sp.rgb.bias.data_ptr(), L.ptr(image),
+                       sp.rgb.upsample.kernel.data_ptr() if image is not None else None, new_image.data_ptr(), batch,
+                       out_h, out_w, stream)
+                image = new_image
+            elif sp.rgb is not None:
                 rs, _ = bc["views"][lp.rgb_job]
                 if g.min_rgb_size <= current_size:
                     image = _torgb(x, sp.rgb.conv.weight, rs, sp.rgb.bias, image,
