@@ -394,8 +394,11 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
   const unsigned grid = (unsigned)(m_tiles * p.n_tiles);
 #define MAUA_TC_LAUNCH(KCV, UPV)                                                                                   \
   do {                                                                                                             \
-    MAUA_CHECK_CUDA(cudaFuncSetAttribute(modconv_tc_kernel<KCV, UPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)smem));                                                              \
+    static size_t smem_set = 0; /* per instantiation; never called again during CUDA-graph capture */            \
+    if (smem > smem_set) {                                                                                         \
+      MAUA_CHECK_CUDA(cudaFuncSetAttribute(modconv_tc_kernel<KCV, UPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+      smem_set = smem;                                                                                             \
+    }                                                                                                              \
     modconv_tc_kernel<KCV, UPV><<<grid, 192, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep);                       \
   } while (0)
   if (kc == 64) {

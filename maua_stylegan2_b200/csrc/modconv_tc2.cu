@@ -378,7 +378,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
                        cudaStream_t st) {
   using namespace tc2;
   const int GH = up ? h + 1 : h, GW = up ? w + 1 : w;
-  if (GH < 4 * TH || GW < 4 * TW) return MAUA_E_UNSUPPORTED;  // <= 32^2: v1's batch-folded tiles fill the SMs better
+  if (GH < TH || GW < 2 * TW) return MAUA_E_UNSUPPORTED;  // 4^2 / 8^2: v1's batch-folded tiles
   Params p;
   p.B = batch; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout; p.GH = GH; p.GW = GW;
   const int nphase = up ? 4 : 1;
@@ -485,8 +485,11 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   }
 #define MAUA_TC2_LAUNCH(KCV, UPV)                                                                                   \
   do {                                                                                                              \
-    MAUA_CHECK_CUDA(cudaFuncSetAttribute(modconv_tc2_kernel<KCV, UPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)smem));                                                               \
+    static size_t smem_set = 0; /* per instantiation; never called again during CUDA-graph capture */            \
+    if (smem > smem_set) {                                                                                         \
+      MAUA_CHECK_CUDA(cudaFuncSetAttribute(modconv_tc2_kernel<KCV, UPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+      smem_set = smem;                                                                                             \
+    }                                                                                                              \
     modconv_tc2_kernel<KCV, UPV><<<(unsigned)grid, THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep);             \
   } while (0)
   if (up) MAUA_TC2_LAUNCH(32, true); else MAUA_TC2_LAUNCH(32, false);

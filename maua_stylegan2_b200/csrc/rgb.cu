@@ -154,23 +154,37 @@ __global__ void __launch_bounds__(256) rgb_weights_kernel(const float* __restric
   wr[i] = v;
 }
 
+// VEC = 4: one thread = 4 consecutive pixels of one (b, k) plane (float4 in / out); the 2x2 live taps of the up-2
+// FIR come from 3 skip columns x 2 skip rows held in registers.  Rounding identical to skip_up2 / torgb_kernel.
+template <int VEC>
 __global__ void __launch_bounds__(256) rgb_finish_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
                                                          const float* __restrict__ skip, const float* __restrict__ k4,
-                                                         float* __restrict__ y, int h, int w, long long total) {
+                                                         float* __restrict__ y, int h, int w, long long total_vec) {
   __shared__ float kf[16];
   if (threadIdx.x < 16) kf[threadIdx.x] = k4 ? __ldg(k4 + threadIdx.x) : 0.f;
   __syncthreads();
-  const long long hw = (long long)h * w;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const long long plane = i / hw;  // b*3 + k
-    const int pidx = (int)(i - plane * hw);
-    const int k = (int)(plane % 3);
-    float o = __fadd_rn(partial[i], bias ? __ldg(bias + k) : 0.f);
-    if (skip) {
-      const int oy = pidx / w, ox = pidx - oy * w;
-      o = __fadd_rn(o, skip_up2(skip + plane * (h >> 1) * (w >> 1), h >> 1, w >> 1, kf, oy, ox));
+  const int wv = w / VEC;
+  const long long hwv = (long long)h * wv;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total_vec; i += (long long)gridDim.x * 256) {
+    const long long plane = i / hwv;  // b*3 + k
+    const int rem = (int)(i - plane * hwv);
+    const int oy = rem / wv, ox0 = (rem - oy * wv) * VEC;
+    const float bb = bias ? __ldg(bias + (int)(plane % 3)) : 0.f;
+    float o[VEC];
+    if (VEC == 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(partial) + i);
+      o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else {
+      o[0] = partial[i];
     }
-    y[i] = o;
+    const float* sp = skip ? skip + plane * (h >> 1) * (w >> 1) : nullptr;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      o[j] = __fadd_rn(o[j], bb);
+      if (skip) o[j] = __fadd_rn(o[j], skip_up2(sp, h >> 1, w >> 1, kf, oy, ox0 + j));
+    }
+    if (VEC == 4) reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    else y[i] = o[0];
   }
 }
 
@@ -250,9 +264,12 @@ extern "C" int maua_rgb_finish_f32(const float* partial, const float* bias, cons
   MAUA_CHECK_ARG(!skip || (k4 && (h % 2 == 0) && (w % 2 == 0)), "rgb_finish: skip needs k4 and even output size");
   const long long total = (long long)batch * 3 * h * w;
   if (total == 0) return MAUA_OK;
-  long long blocks = ceil_div(total, 256LL);
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
-  rgb_finish_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(partial, bias, skip, k4, y, h, w, total);
+  const bool vec = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(partial) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  const long long work = vec ? total / 4 : total;
+  long long blocks = ceil_div(work, 256LL);
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  if (vec) rgb_finish_kernel<4><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(partial, bias, skip, k4, y, h, w, work);
+  else rgb_finish_kernel<1><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(partial, bias, skip, k4, y, h, w, work);
   MAUA_CHECK_LAUNCH("rgb_finish");
   return MAUA_OK;
 }

@@ -34,7 +34,7 @@ class FramePipeline:
     """Batches -> generator -> uint8 NHWC frames in pinned host memory, double-buffered over two CUDA streams."""
 
     def __init__(self, generator, latents, noise, batch_size, truncation=1.0, bends=None, rewrites=None,
-                 randomize_noise=False, device=None, rank=0, world=1):
+                 randomize_noise=False, device=None, rank=0, world=1, use_graph=True):
         self.g = generator
         self.device = device or next(generator.parameters()).device
         self.batch = batch_size
@@ -54,6 +54,56 @@ class FramePipeline:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._host = [None, None]
+        # CUDA graphs: the ~50 launches of a batch are captured once per ping-pong slot and replayed; the host then only
+        # issues the input copies + one graph launch per step (Python + ctypes per launch would otherwise bound e2e).
+        # Per-batch Python objects (bend modulation, rewrites, fresh random noise) cannot be captured -> eager.
+        self.use_graph = (use_graph and not self.bends and not self.rewrites and not randomize_noise)
+        self._graphs = [None, None]
+        self._slot_busy = [None, None]  # per ping-pong slot: (d2h-done event, collective work) still reading its frames
+
+    def _graph_step(self, n, slot):
+        """Copy batch n into the slot's static inputs and replay its captured forward; returns the static uint8 frames."""
+        sl = slice(n, n + self.batch)
+        busy = self._slot_busy[slot]
+        if busy is not None:  # the static output of this slot may still be read by the D2H copy / all-gather of step i-2
+            if busy[0] is not None:
+                torch.cuda.current_stream(self.device).wait_event(busy[0])
+            if busy[1] is not None:
+                busy[1].wait()
+            self._slot_busy[slot] = None
+        gs = self._graphs[slot]
+        if gs is None:
+            # static inputs, one eager warm-up (plan / attribute setup happens here), then capture
+            gs = {"latent": torch.empty((self.batch,) + tuple(self.latents.shape[1:]), device=self.device),
+                  "noise": [None if ns is None else (ns.to(self.device) if ns.shape[0] == 1 else
+                                                     torch.empty((self.batch,) + tuple(ns.shape[1:]), device=self.device))
+                            for ns in self.noise],
+                  "trunc": self.truncation if isinstance(self.truncation, float) else
+                  torch.empty(self.batch, device=self.device)}
+            self._graphs[slot] = gs
+            self._fill_static(gs, sl)
+            run = lambda: self.g(styles=gs["latent"], noise=gs["noise"], truncation=gs["trunc"], transform_dict_list=[],
+                                 randomize_noise=False, input_is_latent=True, return_u8=True)[0]
+            run()
+            torch.cuda.current_stream(self.device).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                gs["out"] = run()
+            gs["graph"] = graph
+        self._fill_static(gs, sl)
+        gs["graph"].replay()
+        return gs["out"]
+
+    def _fill_static(self, gs, sl):
+        gs["latent"].copy_(self.latents[sl], non_blocking=True)
+        self.h2d_bytes += 0 if self.latents.is_cuda else gs["latent"].numel() * 4
+        for dst, ns in zip(gs["noise"], self.noise):
+            if ns is not None and ns.shape[0] != 1:
+                dst.copy_(ns[sl], non_blocking=True)
+                self.h2d_bytes += 0 if ns.is_cuda else dst.numel() * 4
+        if not isinstance(self.truncation, float):
+            gs["trunc"].copy_(self.truncation[sl], non_blocking=True)
+            self.h2d_bytes += gs["trunc"].numel() * 4
 
     def prepare_host_buffers(self, frame_shape, n_per_step=None):
         """Pin the two ping-pong frame buffers up front (pinning 25-200 MB takes milliseconds; keep it out of the loop)."""
@@ -142,12 +192,17 @@ class FramePipeline:
                 consume(p["host"].numpy()[:p["valid"]])
 
         pending = None
-        nxt = self._stage(batch_start(0)) if steps else None
+        graph_ok = self.use_graph
+        nxt = self._stage(batch_start(0)) if (steps and not graph_ok) else None
         for i in range(steps):
-            item = nxt
-            nxt = self._stage(batch_start(i + 1)) if i + 1 < steps else None
             n = batch_start(i)
-            frames = self._render(item, n)
+            full = n + self.batch <= self.n_frames
+            if graph_ok and full:
+                frames = self._graph_step(n, i & 1)
+            else:
+                item = nxt if nxt is not None else self._stage(n)
+                nxt = self._stage(batch_start(i + 1)) if (i + 1 < steps and not graph_ok) else None
+                frames = self._render(item, n)
             if frames.shape[0] < self.batch:  # short tail: pad by repeating the last frame (equal-size collective)
                 frames = torch.cat([frames, frames[-1:].expand(self.batch - frames.shape[0], -1, -1, -1)], 0)
             valid = min(self.n_frames - i * world * self.batch, world * self.batch)
@@ -174,6 +229,10 @@ class FramePipeline:
                 if pending is not None:
                     finish(pending)                 # frames of step i-1 (other ping-pong slot)
                 pending = {"done": done, "host": self._host[slot], "valid": valid}
+                if graph_ok and full:
+                    self._slot_busy[i & 1] = (done if gather is None else None, work)
+            elif graph_ok and full and work is not None:
+                self._slot_busy[i & 1] = (None, work)
         if pending is not None:
             finish(pending)
 
