@@ -321,6 +321,7 @@ def main():
                                  truncation=1.0, rank=rank, world=world)
             if rank == 0:
                 pipe.prepare_host_buffers((SIZE, SIZE, 3))
+            pipe.warmup()  # graph capture / first-touch setup is not part of the steady-state frame loop
             sink_bytes = [0]
 
             def consume(frames):

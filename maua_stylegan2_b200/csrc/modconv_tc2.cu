@@ -378,7 +378,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
                        cudaStream_t st) {
   using namespace tc2;
   const int GH = up ? h + 1 : h, GW = up ? w + 1 : w;
-  if (GH < TH || GW < 2 * TW) return MAUA_E_UNSUPPORTED;  // 4^2 / 8^2: v1's batch-folded tiles
+  if (GH < 4 * TH || GW < 4 * TW) return MAUA_E_UNSUPPORTED;  // <= 32^2 (measured): v1's batch-folded tiles are faster
   Params p;
   p.B = batch; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout; p.GH = GH; p.GW = GW;
   const int nphase = up ? 4 : 1;

@@ -94,6 +94,19 @@ class FramePipeline:
         gs["graph"].replay()
         return gs["out"]
 
+    def warmup(self):
+        """Capture the CUDA graphs of both ping-pong slots (or run one eager batch) before the frame loop starts."""
+        if self.n_frames == 0:
+            return
+        with torch.no_grad():
+            if self.use_graph and self.n_frames >= self.batch:
+                for slot in (0, 1):
+                    self._graph_step(0, slot)
+            else:
+                self._render(self._stage(0), 0)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.h2d_bytes = 0
+
     def _fill_static(self, gs, sl):
         gs["latent"].copy_(self.latents[sl], non_blocking=True)
         self.h2d_bytes += 0 if self.latents.is_cuda else gs["latent"].numel() * 4
@@ -297,6 +310,7 @@ def render(generator, latents, noise, offset, duration, batch_size, out_size, ou
     if hasattr(generator, "module"):  # th.nn.DataParallel wrapper of the reference CLI (generate_audiovisual.py:54-55)
         generator = generator.module
     pipe = FramePipeline(generator, latents, list(noise), batch_size, truncation, bends, rewrites, randomize_noise)
+    pipe.warmup()
 
     def consume(frames):
         if frames.shape[1] == 2048 or frames.shape[2] == 2048:
