@@ -42,6 +42,7 @@ struct Params {
   uint32_t a_plane;      // bytes of one bf16 plane of the halo, rounded up to 1024
   uint32_t tmem_cols;
   int AS;                // TMEM accumulator stages (2 = epilogue of item i overlaps the MMAs of item i+1)
+  int resident_b;        // 1: all 9*n_kchunks weight tiles fit the B ring: loaded once per CTA, never released
   int n_phase;           // accumulator phases per item: 1 same-res, 4 transposed
   int n_items;           // work items = n_tiles * tiles_x * tiles_y * B, walked with stride gridDim.x
 };
@@ -132,6 +133,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (++ia == p.SA) { ia = 0; pa ^= 1; }
 #pragma unroll 1
         for (int t = 0; t < tl.n; ++t) {
+          if (p.resident_b && item != (int)blockIdx.x) break;  // weights already resident in shared memory
           mbar_wait(b_empty + 8 * ib, pb ^ 1);
           mbar_expect_tx(b_full + 8 * ib, p.nprod > 1 ? b_stage : b_half);
           const uint32_t dstb = b_base + ib * b_stage;
@@ -169,8 +171,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll 1
         for (int t = 0; t < tl.n; ++t) {
           const Tap tp = tl.t[t];
-          mbar_wait(b_full + 8 * ib, pb);
-          tc_fence_after();
+          if (!p.resident_b || item == (int)blockIdx.x) {
+            mbar_wait(b_full + 8 * ib, pb);
+            tc_fence_after();
+          }
           const uint64_t dbh = db0 + (uint64_t)ib * b_stage16, dbl = dbh + b_half16;
           uint64_t dah = da_stage + (uint64_t)((uint32_t)(tp.hy * p.HW_ + tp.hx) * ROW >> 4);
           uint32_t acc = acc_stage + (uint32_t)(tp.phase * p.R) * blk_cols;
@@ -197,7 +201,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             acc += blk_cols;
           }
           started |= 1u << tp.phase;
-          umma_commit(b_empty + 8 * ib);
+          if (!p.resident_b) umma_commit(b_empty + 8 * ib);
           if (++ib == p.SB) { ib = 0; pb ^= 1; }
         }
         umma_commit(a_empty + 8 * ia);
@@ -441,7 +445,16 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   const uint32_t a_stage = 2 * p.a_plane, b_stage = 2u * bn * kc * 2u;
   p.SA = (2 * a_stage + 4 * b_stage <= budget) ? 2 : 1;
   int sb = (int)((budget - (uint32_t)p.SA * a_stage) / b_stage);
-  if (sb > 12) sb = 12;
+  // small layers: keep ALL weight tiles of the layer in shared memory for the lifetime of the persistent CTA
+  p.resident_b = (p.n_tiles == 1 && 9 * n_kchunks <= sb && 9 * n_kchunks <= 36) ? 1 : 0;
+  if (!p.resident_b && p.n_tiles == 1 && n_kchunks <= 2 && p.SA == 2 &&
+      9 * n_kchunks <= (int)((budget - a_stage) / b_stage)) {  // trade the second A stage for resident weights
+    p.SA = 1;
+    sb = (int)((budget - a_stage) / b_stage);
+    p.resident_b = 1;
+  }
+  if (p.resident_b) sb = 9 * n_kchunks;
+  else if (sb > 12) sb = 12;
   if (sb < 2) return MAUA_E_UNSUPPORTED;
   p.SB = sb;
   const size_t smem = (size_t)p.SA * a_stage + (size_t)p.SB * b_stage + 8 * (2 * p.SA + 2 * p.SB + 6) + 1024;
@@ -462,8 +475,8 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   const long long grid = items < n_sm ? items : n_sm;
   static const bool debug = [] { const char* e = getenv("MAUA_TC_DEBUG"); return e && e[0] == '1'; }();
   if (debug)
-    fprintf(stderr, "[modconv_tc2] %s B%d %d->%d @%dx%d: R=%d BN=%d cat=%d AS=%d SA=%d SB=%d smem=%zuKB tmem=%u items=%lld grid=%lld\n",
-            up ? "up" : "same", batch, cin, cout, h, w, R, bn, p.cat, p.AS, p.SA, p.SB, smem / 1024, p.tmem_cols, items, grid);
+    fprintf(stderr, "[modconv_tc2] %s B%d %d->%d @%dx%d: R=%d BN=%d cat=%d resB=%d AS=%d SA=%d SB=%d smem=%zuKB tmem=%u items=%lld grid=%lld\n",
+            up ? "up" : "same", batch, cin, cout, h, w, R, bn, p.cat, p.resident_b, p.AS, p.SA, p.SB, smem / 1024, p.tmem_cols, items, grid);
 
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   const auto swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
