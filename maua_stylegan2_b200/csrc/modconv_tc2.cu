@@ -143,8 +143,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ================================ MMA issuer ================================
+    // the whole warp walks the loop (uniform control flow); one elected lane issues the tcgen05 instructions
+    const bool leader = elect_one_sync();
     // The issue loop must stay far below the ~50 cycles a 128x32x16 MMA occupies the tensor pipe: all descriptor
     // fields are folded into per-stage base values up front; per MMA only 64-bit adds of small constants remain.
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN);
@@ -182,7 +184,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll 1
           for (int r = 0; r < p.R; ++r) {
             const uint64_t dal = dah + a_plane16;
-            if (mode == 2) {  // [hi*hi | hi*lo] in one N = 2*BN MMA (B stage = hi rows followed by lo rows), then lo*hi
+            if (!leader) {
+            } else if (mode == 2) {  // [hi*hi | hi*lo] in one N = 2*BN MMA (B stage = hi rows followed by lo rows), then lo*hi
               umma_bf16(acc, dah, dbh, idesc2, first);
               umma_bf16(acc, dah + 2, dbh + 2, idesc2, 1u);
               umma_bf16(acc, dal, dbh, idesc, 1u);
@@ -201,13 +204,13 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             acc += blk_cols;
           }
           started |= 1u << tp.phase;
-          if (!p.resident_b) umma_commit(b_empty + 8 * ib);
+          if (!p.resident_b && leader) umma_commit(b_empty + 8 * ib);
           if (++ib == p.SB) { ib = 0; pb ^= 1; }
         }
-        umma_commit(a_empty + 8 * ia);
+        if (leader) umma_commit(a_empty + 8 * ia);
         if (++ia == p.SA) { ia = 0; pa ^= 1; }
       }
-      umma_commit(acc_full + 8 * as);
+      if (leader) umma_commit(acc_full + 8 * as);
       if (++as == p.AS) { as = 0; pacc ^= 1; }
     }
   } else if (warp >= 2) {
@@ -447,12 +450,6 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   int sb = (int)((budget - (uint32_t)p.SA * a_stage) / b_stage);
   // small layers: keep ALL weight tiles of the layer in shared memory for the lifetime of the persistent CTA
   p.resident_b = (p.n_tiles == 1 && 9 * n_kchunks <= sb && 9 * n_kchunks <= 36) ? 1 : 0;
-  if (!p.resident_b && p.n_tiles == 1 && n_kchunks <= 2 && p.SA == 2 &&
-      9 * n_kchunks <= (int)((budget - a_stage) / b_stage)) {  // trade the second A stage for resident weights
-    p.SA = 1;
-    sb = (int)((budget - a_stage) / b_stage);
-    p.resident_b = 1;
-  }
   if (p.resident_b) sb = 9 * n_kchunks;
   else if (sb > 12) sb = 12;
   if (sb < 2) return MAUA_E_UNSUPPORTED;
