@@ -151,9 +151,13 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         if (++ib == p.SB) { ib = 0; pb ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ================================ MMA issuer ================================
+    // whole warp, uniform control flow; one elected lane issues (keeps descriptors in uniform registers)
+    const bool leader = elect_one_sync();
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN);
+    const uint64_t da0 = make_kmajor_desc(a_base, ROW_BYTES), db0 = make_kmajor_desc(b_base, ROW_BYTES);
+    const uint64_t a_stage16 = A_STAGE >> 4, a_half16 = A_HALF >> 4, b_stage16 = b_stage >> 4, b_half16 = b_half >> 4;
     int ia = 0, ib = 0, cur_a = 0;
     uint32_t pa = 0, pb = 0, started = 0;
     for (int kc = 0; kc < p.n_kchunks; ++kc) {
@@ -167,28 +171,27 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         }
         mbar_wait(b_full + 8 * ib, pb);
         tc_fence_after();
-        const uint32_t a_hi = a_base + cur_a * A_STAGE, a_lo = a_hi + A_HALF;
-        const uint32_t b_hi = b_base + ib * b_stage, b_lo = b_hi + b_half;
+        const uint64_t dah = da0 + (uint64_t)cur_a * a_stage16, dal = dah + a_half16;
+        const uint64_t dbh = db0 + (uint64_t)ib * b_stage16, dbl = dbh + b_half16;
         const uint32_t acc = tmem_base + (uint32_t)s.phase * (uint32_t)p.BN;
-        uint32_t accumulate = (started >> s.phase) & 1u;
-#pragma unroll 1
-        for (int prod = 0; prod < p.nprod; ++prod) {
-          const uint64_t da = make_kmajor_desc(prod == 2 ? a_lo : a_hi, ROW_BYTES);
-          const uint64_t db = make_kmajor_desc(prod == 1 ? b_lo : b_hi, ROW_BYTES);
+        const uint32_t first = (started >> s.phase) & 1u;
+        if (leader) {
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k) {
-            // advancing K by 16 bf16 = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
-            umma_bf16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
-            accumulate = 1;
+          for (int k = 0; k < KC / 16; ++k) umma_bf16(acc, dah + 2 * k, dbh + 2 * k, idesc, k == 0 ? first : 1u);
+          if (p.nprod > 1) {
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) umma_bf16(acc, dah + 2 * k, dbl + 2 * k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) umma_bf16(acc, dal + 2 * k, dbh + 2 * k, idesc, 1u);
           }
+          umma_commit(b_empty + 8 * ib);
+          if (s.a_last) umma_commit(a_empty + 8 * cur_a);
         }
         started |= 1u << s.phase;
-        umma_commit(b_empty + 8 * ib);
-        if (s.a_last) umma_commit(a_empty + 8 * cur_a);
         if (++ib == p.SB) { ib = 0; pb ^= 1; }
       }
     }
-    umma_commit(acc_full);
+    if (leader) umma_commit(acc_full);
   } else if (warp >= 2) {
     // ================================ epilogue ================================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
