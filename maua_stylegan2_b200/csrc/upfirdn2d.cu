@@ -12,6 +12,8 @@
 //                        (+3 halo) is staged in shared memory with coalesced loads, every thread produces a
 //                        4 x RY register block from LDS.128 rows and emits float4 stores.
 //   generic_kernel     — everything else (polyphase up/down, large kernels, minor > 1): one thread per output.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace maua {
@@ -25,8 +27,8 @@ struct UfdParams {
 // ---------------------------------------------------------------------------------------------------------------
 // identity-rate tiled kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int TW, int RY>
-__global__ void __launch_bounds__(256) blur_tile_kernel(const float* __restrict__ x, float* __restrict__ y,
+template <int TW, int RY, int MINB>
+__global__ void __launch_bounds__(256, MINB) blur_tile_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                         const float* __restrict__ k, UfdParams p, int vec_store) {
   constexpr int TXN = TW / 4;        // threads along x
   constexpr int TYN = 256 / TXN;     // thread rows
@@ -57,20 +59,35 @@ __global__ void __launch_bounds__(256) blur_tile_kernel(const float* __restrict_
     const float* xp = x + plane * (long long)p.in_h * p.in_w;
     __syncthreads();  // previous iteration's readers are done (also orders skf)
     {
-      // row-per-warp staging: no integer division, one bounds test per row, coalesced 128-byte warp loads
+      // row-per-warp staging: no integer division, one bounds test per row, coalesced 128-byte warp loads; every
+      // thread issues ALL its loads (up to RPW x CPL) before the first shared-memory store, so ~20 independent
+      // requests per thread are in flight instead of ~5 (the kernel was latency-bound at 56 % of HBM peak)
+      constexpr int RPW = (ROWS + 7) / 8;    // rows per warp
+      constexpr int CPL = (COLS + 31) / 32;  // columns per lane
       const int lane = tid & 31, wrp = tid >> 5;
-#pragma unroll 1
-      for (int r = wrp; r < ROWS; r += 8) {
-        const int iy = iy0 + r;
-        const bool row_ok = (iy >= 0) && (iy < p.in_h);
-        const float* src = xp + (long long)iy * p.in_w + ix0;
-        float* dst = sx + r * PITCH;
+      float v[RPW][CPL];
 #pragma unroll
-        for (int c = lane; c < COLS; c += 32) {
+      for (int i = 0; i < RPW; ++i) {
+        const int r = wrp + 8 * i;
+        const int iy = iy0 + r;
+        const bool row_ok = (r < ROWS) && (iy >= 0) && (iy < p.in_h);
+        const float* src = xp + (long long)iy * p.in_w + ix0;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const int c = lane + 32 * j;
           const int ix = ix0 + c;
-          float v = 0.f;
-          if (row_ok && ix >= 0 && ix < p.in_w) v = __ldg(src + c);
-          dst[c] = v;
+          v[i][j] = (row_ok && c < COLS && ix >= 0 && ix < p.in_w) ? __ldg(src + c) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const int r = wrp + 8 * i;
+        if (r < ROWS) {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) {
+            const int c = lane + 32 * j;
+            if (c < COLS) sx[r * PITCH + c] = v[i][j];
+          }
         }
       }
     }
@@ -96,14 +113,10 @@ __global__ void __launch_bounds__(256) blur_tile_kernel(const float* __restrict_
       for (int j = 0; j < RY; ++j) {
         const int ky = r - j;
         if (ky >= 0 && ky < 4) {
-// outputs (0,1) and (2,3) advance together: two packed FMAs per tap, kx ascending per output (order kept)
 #pragma unroll
-          for (int kx = 0; kx < 4; ++kx) {
-            const float2 kv = make_float2(kf[ky * 4 + kx], kf[ky * 4 + kx]);
-            const float2 a01 = ffma2(make_float2(row[kx], row[kx + 1]), kv, make_float2(acc[j][0], acc[j][1]));
-            const float2 a23 = ffma2(make_float2(row[kx + 2], row[kx + 3]), kv, make_float2(acc[j][2], acc[j][3]));
-            acc[j][0] = a01.x; acc[j][1] = a01.y; acc[j][2] = a23.x; acc[j][3] = a23.y;
-          }
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) acc[j][i] = __fmaf_rn(row[i + kx], kf[ky * 4 + kx], acc[j][i]);
         }
       }
     }
@@ -181,15 +194,23 @@ extern "C" int maua_upfirdn2d_f32(const float* x, float* y, const float* k, int 
   if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && kh <= 4 && kw <= 4 && minor == 1) {
     const int vec = ((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (p.out_w & 3) == 0) ? 1 : 0;
     const int planes_y = major < 32768 ? major : 32768;
+    static const int variant = [] { const char* e = getenv("MAUA_UFD_VARIANT"); return e ? atoi(e) : 0; }();
+#define MAUA_BLUR_LAUNCH(TWV, RYV, MINBV)                                                    \
+  do {                                                                                       \
+    constexpr int TH = (256 / (TWV / 4)) * RYV;                                              \
+    dim3 grid(ceil_div(p.out_w, TWV) * ceil_div(p.out_h, TH), planes_y);                     \
+    blur_tile_kernel<TWV, RYV, MINBV><<<grid, 256, 0, st>>>(x, y, k, p, vec);                \
+  } while (0)
     if (p.out_w > 64) {
-      constexpr int TW = 128, RY = 4, TH = (256 / (TW / 4)) * RY;
-      dim3 grid(ceil_div(p.out_w, TW) * ceil_div(p.out_h, TH), planes_y);
-      blur_tile_kernel<TW, RY><<<grid, 256, 0, st>>>(x, y, k, p, vec);
+      // measured on B200, [4,32,2049,2049]: (128,4) tiles at 5 CTAs/SM 4.60 TB/s | 4 CTAs 4.24 | (128,8)x2 3.43 |
+      // (64,4)x4 3.92 | (128,2)x6 3.93   (MAUA_UFD_VARIANT keeps the alternatives reachable for re-tuning)
+      if (variant == 1) MAUA_BLUR_LAUNCH(128, 4, 4);
+      else if (variant == 2) MAUA_BLUR_LAUNCH(128, 4, 6);
+      else MAUA_BLUR_LAUNCH(128, 4, 5);
     } else {
-      constexpr int TW = 32, RY = 2, TH = (256 / (TW / 4)) * RY;
-      dim3 grid(ceil_div(p.out_w, TW) * ceil_div(p.out_h, TH), planes_y);
-      blur_tile_kernel<TW, RY><<<grid, 256, 0, st>>>(x, y, k, p, vec);
+      MAUA_BLUR_LAUNCH(32, 2, 4);
     }
+#undef MAUA_BLUR_LAUNCH
     MAUA_CHECK_LAUNCH("upfirdn2d(blur_tile)");
     return MAUA_OK;
   }

@@ -8,6 +8,7 @@ hdr, data = rows[0], rows[2:]
 C = {h: i for i, h in enumerate(hdr)}
 cols = [
     ("kernel", "Kernel Name"), ("grid", "Grid Size"), ("us", "gpu__time_duration.sum"),
+    ("tc_pipe%", "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed"),
     ("tensor%", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
     ("hmma_ops%", "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed"),
     ("dram_rd_MB", "dram__bytes_read.sum"), ("dram_wr_MB", "dram__bytes_write.sum"),
