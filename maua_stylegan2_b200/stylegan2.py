@@ -6,7 +6,7 @@ transform_dict_list, input_is_latent, ...)` call signature, so `render.render` /
 can use it as-is.  What runs underneath is different: `Generator.forward` does not call the sub-modules one by
 one; it drives libmaua_b200.so through the C ABI (include/maua_b200.h):
 
-  style prologue (1 launch: truncation + 26 affines + demod)  ->  per layer:
+  style prologue (2 launches: truncation + 26 affines, 17 demod vectors)  ->  per layer:
      impl="tc"   tcgen05 implicit-GEMM conv on NHWC split-bf16 activations with the noise/bias/lrelu/next-style
                  epilogue fused (up layers: 4-phase transposed conv + NHWC blur/activation kernel)
      impl="simt" fp32 SIMT conv -> upfirdn2d blur -> noise+bias+lrelu (reference op order, exact fp32)
