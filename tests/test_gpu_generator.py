@@ -128,3 +128,61 @@ def test_network_bend_changes_shape_like_reference(impl):
     assert rel_err(img.cpu().numpy(), ref_img.numpy()) < TOL[impl]
     for a, r in zip(acts, ref_acts):
         assert a.shape == r.shape and rel_err(a.cpu().numpy(), r.numpy()) < TOL[impl]
+
+
+def test_generator_1024_configf_vs_oracle():
+    """BASELINE.json configs[1] architecture (1024x1024 config-f, channel_multiplier=2) at full size, one frame:
+    every layer of the bench workload (halo conv R/BN/concat policies, fused ToRGB, TMA blur) against the CPU oracle."""
+    size, cm, seed, b = 1024, 2, 0, 1
+    g, sd = make_generator(size, cm, seed, "tc")
+    log_size, num_layers, n_latent = O.layout(size)
+    rng = np.random.Generator(np.random.PCG64(2))
+    latent = torch.from_numpy(rng.standard_normal((b, n_latent, 512)).astype(np.float32)) * 0.5
+    noise = [torch.from_numpy(rng.standard_normal((b, 1, 2 ** ((l + 5) // 2), 2 ** ((l + 5) // 2))).astype(np.float32))
+             if 2 ** ((l + 5) // 2) <= 256 else None for l in range(num_layers)]   # default hooks: buffers above 256
+    tl = torch.zeros(1, 512)
+    with torch.no_grad():
+        ref_img, ref_acts = O.generator_forward(sd, size, latent, noise, 0.9, tl, channel_multiplier=cm)
+        g.truncation_latent = tl.cuda()
+        img, acts = g(latent.cuda(), noise=[n.cuda() if n is not None else None for n in noise], truncation=0.9,
+                      input_is_latent=True, randomize_noise=False, return_activation_maps=True)
+        img2, _ = g(latent.cuda(), noise=[n.cuda() if n is not None else None for n in noise], truncation=0.9,
+                    input_is_latent=True, randomize_noise=False)       # fused-ToRGB / no-fp32-map path
+    errs = [rel_err(a.cpu().numpy(), r.numpy()) for a, r in zip(acts, ref_acts)]
+    e1, e2 = rel_err(img.cpu().numpy(), ref_img.numpy()), rel_err(img2.cpu().numpy(), ref_img.numpy())
+    print(f"1024 tc: image {e1:.2e} / fused {e2:.2e} acts {['%.1e' % e for e in errs]}")
+    assert max(errs) < TOL["tc"] and e1 < TOL["tc"] and e2 < TOL["tc"]
+
+
+def test_generator_512_confige_bend_and_truncation_sweep():
+    """BASELINE.json configs[3] shape: 512x512 config-e (channel_multiplier=1), a translation bend on layer 6 driven by a
+    per-frame modulation and a per-frame truncation sweep; kornia is absent, so the bend is an integer torch.roll
+    (same contract: a `transform(modulation_batch) -> nn.Module` factory), checked against the oracle."""
+    size, cm, seed, b = 512, 1, 4, 2
+    g, sd = make_generator(size, cm, seed, "tc")
+
+    class Roll(torch.nn.Module):
+        def __init__(self, shifts):
+            super().__init__()
+            self.shifts = shifts
+
+        def forward(self, x):
+            return torch.stack([torch.roll(xi, int(s), dims=2) for xi, s in zip(x, self.shifts)])
+
+    modulation = torch.tensor([3.0, 11.0])
+    bends = [{"layer": 6, "transform": Roll(modulation)}]
+    log_size, num_layers, n_latent = O.layout(size)
+    rng = np.random.Generator(np.random.PCG64(5))
+    latent = torch.from_numpy(rng.standard_normal((b, n_latent, 512)).astype(np.float32)) * 0.5
+    noise = [torch.from_numpy(rng.standard_normal((b, 1, 2 ** ((l + 5) // 2), 2 ** ((l + 5) // 2))).astype(np.float32))
+             for l in range(num_layers)]
+    psi = torch.tensor([0.55, 0.95])
+    tl = torch.from_numpy(rng.standard_normal((1, 512)).astype(np.float32)) * 0.1
+    with torch.no_grad():
+        ref_img, ref_acts = O.generator_forward(sd, size, latent, noise, psi, tl, channel_multiplier=cm, bends=bends)
+        g.truncation_latent = tl.cuda()
+        img, acts = g(latent.cuda(), noise=[n.cuda() for n in noise], truncation=psi.cuda(), input_is_latent=True,
+                      transform_dict_list=bends, return_activation_maps=True)
+    assert img.shape == (b, 3, 512, 512)
+    errs = [rel_err(a.cpu().numpy(), r.numpy()) for a, r in zip(acts, ref_acts)]
+    assert max(errs) < TOL["tc"] and rel_err(img.cpu().numpy(), ref_img.numpy()) < TOL["tc"]
