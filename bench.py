@@ -380,7 +380,8 @@ def main():
                         "algorithmic_gflop_per_launch_set": conv_fl / nprof / 1e9,
                         "products_per_mac": nprod, "issued_frac": nprod * ach / pk["bf16_tflops_sustained"],
                         "ms_per_step": conv_ms / nprof,
-                        "per_layer_tflops": {k: round(v[1] / (v[0] * 1e-3) / 1e12, 2) for k, v in per_layer.items()}}
+                        "per_layer_tflops": {k: round(v[1] / (v[0] * 1e-3) / 1e12, 2) for k, v in per_layer.items()},
+                        "per_layer_ms": {k: round(v[0] / nprof, 4) for k, v in per_layer.items()}}
             # standalone upfirdn2d (the public op) on the largest Blur of the frame: [B,32,2049,2049] -> [B,32,2048,2048]
             from maua_stylegan2_b200 import op
 

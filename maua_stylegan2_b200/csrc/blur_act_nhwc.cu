@@ -9,6 +9,8 @@
 // HBM-bound: 4 B/elt in, 4 B/elt out.  One CTA = 16x16 output pixels x 32 channels; the 19x19x32 input tile
 // is staged in shared memory with 128-byte-contiguous loads; each thread slides down a column of 8 outputs for
 // one float4 of channels (44 LDS.128 per 8 outputs), stores are 8-byte bf16x4 per plane.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "tmap.cuh"
@@ -128,7 +130,9 @@ __device__ __forceinline__ void tma_load_tile_4d(uint32_t dst, const CUtensorMap
   ptx::tma_load_4d(dst, m, bar, c0, c1, c2, c3);
 }
 
-__global__ void __launch_bounds__(256, 2) blur_act_nhwc_tma_kernel(const __grid_constant__ CUtensorMap tm_u,
+// RPT = output rows per thread (8: 256 threads, 4: 512 threads — more warps to hide LDS / epilogue latency)
+template <int RPT>
+__global__ void __launch_bounds__(128 * (16 / RPT), 2) blur_act_nhwc_tma_kernel(const __grid_constant__ CUtensorMap tm_u,
                                                                    const float* __restrict__ k4, MauaConvEpilogue ep,
                                                                    int batch, int ch, int hu, int wu, int n_tiles) {
   using namespace ptx;
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_tma_kernel(const __grid_
   const int c4 = tid & 7;
   const int p = tid >> 3;
   const int lx = p & 15;
-  const int ly0 = (p >> 4) * 8;
+  const int ly0 = (p >> 4) * RPT;
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(ep.out_hi);
   __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(ep.out_lo);
   const float nw = (ep.activate && ep.noise) ? __ldg(ep.noise_weight) : 0.f;
@@ -196,32 +200,32 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_tma_kernel(const __grid_
     const int cbase = cg * BCH + c4 * 4;
     const int ox = ox0 + lx;
     float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), sn = make_float4(1.f, 1.f, 1.f, 1.f);
-    float nzv[8];
+    float nzv[RPT];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) nzv[j] = 0.f;
+    for (int j = 0; j < RPT; ++j) nzv[j] = 0.f;
     if (ox < ow) {
       if (ep.activate && ep.bias) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + cbase));
       if (ep.s_next) sn = __ldg(reinterpret_cast<const float4*>(ep.s_next + (long long)b * ch + cbase));
       if (ep.activate && ep.noise) {
         const float* np = ep.noise + (long long)b * ep.noise_bstride + (long long)(oy0 + ly0) * ow + ox;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < RPT; ++j)
           if (oy0 + ly0 + j < oh) nzv[j] = __ldg(np + (long long)j * ow);
       }
     }
     mbar_wait(bar0 + 8 * stage, (it >> 1) & 1);
     const float* tile = tile_ptr[stage];
-    float4 acc[8];
+    float4 acc[RPT];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < RPT; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int r = 0; r < 11; ++r) {
+    for (int r = 0; r < RPT + 3; ++r) {
       float4 row[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e)
         row[e] = *reinterpret_cast<const float4*>(&tile[((ly0 + r) * BIN + lx + e) * BCH + c4 * 4]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < RPT; ++j) {
         const int a = r - j;
         if (a >= 0 && a < 4) {
 #pragma unroll
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(256, 2) blur_act_nhwc_tma_kernel(const __grid_
 
     if (ox >= ow) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < RPT; ++j) {
       const int oy = oy0 + ly0 + j;
       if (oy >= oh) break;
       float v0 = acc[j].x, v1 = acc[j].y, v2 = acc[j].z, v3 = acc[j].w;
@@ -297,14 +301,18 @@ extern "C" int maua_blur_act_nhwc(const float* u, const float* k4, const MauaCon
     const long long n_tiles = (long long)ceil_div(ow, BT) * ceil_div(oh, BT) * (ch / BCH) * batch;
     MAUA_CHECK_ARG(n_tiles < (1LL << 31), "blur_act_nhwc: too many tiles");
     const size_t smem = 2 * (size_t)BIN * BIN * BCH * 4 + 16 + 128;
+    static const int rpt = [] { const char* e = getenv("MAUA_BLUR_RPT"); return e ? atoi(e) : 8; }();
     static bool attr_done = false;
     if (!attr_done) {
-      MAUA_CHECK_CUDA(cudaFuncSetAttribute(blur_act_nhwc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
+      MAUA_CHECK_CUDA(cudaFuncSetAttribute(blur_act_nhwc_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MAUA_CHECK_CUDA(cudaFuncSetAttribute(blur_act_nhwc_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_done = true;
     }
     const int grid = (int)(n_tiles < 148 * 2 ? n_tiles : 148 * 2);
-    blur_act_nhwc_tma_kernel<<<grid, 256, smem, as_stream(stream)>>>(tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles);
+    if (rpt == 8)
+      blur_act_nhwc_tma_kernel<8><<<grid, 256, smem, as_stream(stream)>>>(tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles);
+    else
+      blur_act_nhwc_tma_kernel<4><<<grid, 512, smem, as_stream(stream)>>>(tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles);
     MAUA_CHECK_LAUNCH("blur_act_nhwc(tma)");
     return MAUA_OK;
   }

@@ -43,18 +43,28 @@ struct Params {
   uint32_t tmem_cols;
   int AS;                // TMEM accumulator stages (2 = epilogue of item i overlaps the MMAs of item i+1)
   int resident_b;        // 1: all 9*n_kchunks weight tiles fit the B ring: loaded once per CTA, never released
-  int n_phase;           // accumulator phases per item: 1 same-res, 4 transposed
+  int n_phase;           // accumulator phases per item: 1 same-res; transposed: 4 / 2 / 1 (4 / n_groups)
+  int n_groups;          // transposed only: phase groups walked as separate work items (1, 2 or 4)
   int n_items;           // work items = n_tiles * tiles_x * tiles_y * B, walked with stride gridDim.x
 };
 
 // Tap lists.  same-res: tap (ky,kx) reads x[y+ky-1, x+kx-1] -> halo (ky, kx), one accumulator phase.
 // transposed: u[2y'+py, 2x'+px] += W[ky,kx] * x[y'+dy, x'+dx], py = ky&1, dy = (ky==2 ? -1 : 0) -> halo row dy+1;
 // the four sub-pixel phases (py,px) accumulate side by side in TMEM and share the one halo load.
-struct Tap { int8_t hy, hx, tap, phase; };
+struct Tap { int8_t hy, hx, tap, phase; };  // phase = accumulator index LOCAL to the work item
 struct TapList { int32_t n; Tap t[9]; };
-__constant__ TapList c_taps[2] = {
+// [0] same-res; transposed: [1] all four phases in one item; [2..3] two phase groups {0,1} / {2,3};
+// [4..7] one phase per item.  Phase splitting trades extra halo loads (cheap) for fewer accumulator columns per item,
+// i.e. room for two accumulator stages (epilogue overlap) and/or a wider N tile.
+__constant__ TapList c_taps[8] = {
     {9, {{0, 0, 0, 0}, {0, 1, 1, 0}, {0, 2, 2, 0}, {1, 0, 3, 0}, {1, 1, 4, 0}, {1, 2, 5, 0}, {2, 0, 6, 0}, {2, 1, 7, 0}, {2, 2, 8, 0}}},
-    {9, {{1, 1, 0, 0}, {1, 1, 1, 1}, {1, 0, 2, 0}, {1, 1, 3, 2}, {1, 1, 4, 3}, {1, 0, 5, 2}, {0, 1, 6, 0}, {0, 1, 7, 1}, {0, 0, 8, 0}}}};
+    {9, {{1, 1, 0, 0}, {1, 1, 1, 1}, {1, 0, 2, 0}, {1, 1, 3, 2}, {1, 1, 4, 3}, {1, 0, 5, 2}, {0, 1, 6, 0}, {0, 1, 7, 1}, {0, 0, 8, 0}}},
+    {6, {{1, 1, 0, 0}, {1, 0, 2, 0}, {0, 1, 6, 0}, {0, 0, 8, 0}, {1, 1, 1, 1}, {0, 1, 7, 1}}},  // phases 0,1
+    {3, {{1, 1, 3, 0}, {1, 0, 5, 0}, {1, 1, 4, 1}}},                                            // phases 2,3
+    {4, {{1, 1, 0, 0}, {1, 0, 2, 0}, {0, 1, 6, 0}, {0, 0, 8, 0}}},                              // phase 0
+    {2, {{1, 1, 1, 0}, {0, 1, 7, 0}}},                                                          // phase 1
+    {2, {{1, 1, 3, 0}, {1, 0, 5, 0}}},                                                          // phase 2
+    {1, {{1, 1, 4, 0}}}};                                                                       // phase 3
 
 __device__ __forceinline__ float lrelu_s(float v, float slope, float scale) { return (v > 0.f ? v : v * slope) * scale; }
 
@@ -101,19 +111,23 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // work item -> (n tile, pixel tile); n fastest: concurrently running CTAs share the activation halo through L2
-  auto decode = [&](int item, int& n0, int& x0, int& y0, int& b) {
+  // work item -> (n tile, phase group, pixel tile); n fastest, then group: concurrently running CTAs share the halo
+  // through L2
+  auto decode = [&](int item, int& n0, int& grp, int& x0, int& y0, int& b) {
     const int n_tile = item % p.n_tiles;
-    const int rest = item / p.n_tiles;
+    int rest = item / p.n_tiles;
+    grp = rest % p.n_groups;
+    rest /= p.n_groups;
     x0 = (rest % p.tiles_x) * TW;
     y0 = ((rest / p.tiles_x) % p.tiles_y) * TH * p.R;
     b = rest / (p.tiles_x * p.tiles_y);
     n0 = n_tile * p.BN;
   };
-  constexpr int NPH = UP ? 4 : 1;
-  const TapList& tl = c_taps[UP ? 1 : 0];
+  auto tap_list = [&](int grp) -> const TapList& {
+    return c_taps[!UP ? 0 : (p.n_groups == 1 ? 1 : (p.n_groups == 2 ? 2 + grp : 4 + grp))];
+  };
   const uint32_t blk_cols = (uint32_t)(p.cat ? 2 * p.BN : p.BN);  // TMEM columns of one accumulator
-  const uint32_t acc_cols = (uint32_t)(NPH * p.R) * blk_cols;     // ... of one accumulator stage
+  const uint32_t acc_cols = (uint32_t)(p.n_phase * p.R) * blk_cols;  // ... of one accumulator stage
   const uint32_t halo_bytes = (uint32_t)(p.HW_ * p.HH_) * ROW;    // bytes one TMA box writes per plane
 
   if (warp == 0 && lane == 0) {
@@ -121,8 +135,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      int n0, x0, y0, b;
-      decode(item, n0, x0, y0, b);
+      int n0, grp, x0, y0, b;
+      decode(item, n0, grp, x0, y0, b);
+      const TapList& tl = tap_list(grp);
       for (int kc = 0; kc < p.n_kchunks; ++kc) {
         const int c0 = kc * KC;
         mbar_wait(a_empty + 8 * ia, pa ^ 1);
@@ -161,8 +176,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     int ia = 0, ib = 0, as = 0;
     uint32_t pa = 0, pb = 0, pacc = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      int n0, x0, y0, b;
-      decode(item, n0, x0, y0, b);
+      int n0, grp, x0, y0, b;
+      decode(item, n0, grp, x0, y0, b);
+      const TapList& tl = tap_list(grp);
       mbar_wait(acc_empty + 8 * as, pacc ^ 1);  // epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t acc_stage = tmem_base + (uint32_t)as * acc_cols;
@@ -225,8 +241,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     int as = 0;
     uint32_t pacc = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      int n0, x0, y0, b;
-      decode(item, n0, x0, y0, b);
+      int n0, grp, x0, y0, b;
+      decode(item, n0, grp, x0, y0, b);
       const int gx = x0 + tx;
       mbar_wait(acc_full + 8 * as, pacc);
       tc_fence_after();
@@ -242,12 +258,13 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const int gy = y0 + r * TH + ty;
         const bool in_grid = (gy < p.GH) && (gx < p.GW);
 #pragma unroll 1
-        for (int ph = 0; ph < NPH; ++ph) {
+        for (int ph = 0; ph < p.n_phase; ++ph) {
+        const int gph = UP ? grp * p.n_phase + ph : 0;  // global sub-pixel phase (py, px) = (gph >> 1, gph & 1)
         int oy, ox, OH, OW;
         bool valid;
         if (UP) {
           OH = 2 * p.H + 1; OW = 2 * p.W + 1;
-          oy = 2 * gy + (ph >> 1); ox = 2 * gx + (ph & 1);
+          oy = 2 * gy + (gph >> 1); ox = 2 * gx + (gph & 1);
           valid = in_grid && oy < OH && ox < OW;
         } else {
           OH = p.H; OW = p.W; oy = gy; ox = gx; valid = in_grid;
@@ -397,39 +414,85 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   // accumulator stages fit (2*R*nphase*BN <= 512) the epilogue of item i overlaps the MMAs of item i+1.
   const int tmem_cap = 512;
   const uint32_t budget = 212u * 1024u;
-  // Pick (R, BN): minimise L2->SMEM bytes per tensor-pipe cycle,
-  //   bytes/cycle ~ [ (16R+2)*10/9 + BN ] / (R*BN)      (A halo amortised over 9 taps + one B tile per tap)
-  // subject to TMEM columns, shared memory (A halo + >= 2 B stages) and a grid that covers the 148 SMs.
-  int best_r = 0, best_bn = 0, best_cat = 0;
-  double best_cost = 1e30;
-  long long best_ctas = 0;
-  for (int r = 4; r >= 1; r >>= 1) {
-    if (r > rows16) continue;
-    for (int bn = 256; bn >= 16; bn >>= 1) {
-      if (cout % bn != 0) continue;
-      if (ep.rgb_out && bn != cout) continue;  // fused ToRGB needs every output channel in one CTA
-      for (int cat = 0; cat <= ((n_products > 1 && bn <= 64) ? 1 : 0); ++cat) {
-        const int blk = cat ? 2 * bn : bn;  // concat mode doubles the accumulator width
-        if (r * blk * nphase > tmem_cap) continue;
-        const uint32_t plane = align1k((uint32_t)((TH * r + (up ? 1 : 2)) * (up ? TW + 1 : TW + 2) * kc * 2));
-        const uint32_t b_st = 2u * bn * kc * 2u;
-        if (2 * plane + 4 * b_st > budget) continue;  // A halo (hi+lo) + a B ring deep enough to hide TMA latency
-        const long long ctas = tiles_x * ceil_div(rows16, (long long)r) * batch * (cout / bn);
-        // modelled tensor-pipe cycles per MMA of N columns: max(math N/2, operand fetch (4 KB A + 32N B) / 128 B/clk,
-        // ~40 cycles of issue overhead); a single accumulator stage exposes the epilogue (penalty); L2->SMEM bytes
-        // per cycle [ (16R+2)*10/9 + BN ] / (R*BN) as a secondary term
-        auto mma_cycles = [](double n) { double c = n / 2.0; if (32.0 + n / 4.0 > c) c = 32.0 + n / 4.0; if (c < 40.0) c = 40.0; return c; };
-        const double per_kstep = cat ? mma_cycles(2.0 * bn) + mma_cycles(bn) : (n_products > 1 ? 3.0 : 1.0) * mma_cycles(bn);
-        const double traffic = ((TH * r + 2) * 10.0 / 9.0 + bn) / ((double)r * bn);
-        const double cost = per_kstep / bn * (2 * r * blk * nphase <= 512 ? 1.0 : 1.35) + 0.15 * traffic;
-        const bool enough = ctas >= 2 * 148, best_enough = best_ctas >= 2 * 148;
-        const bool better = best_r == 0 || (enough && !best_enough) ||
-                            (enough == best_enough && (enough ? cost < best_cost : ctas > best_ctas));
-        if (better) { best_r = r; best_bn = bn; best_cat = cat; best_cost = cost; best_ctas = ctas; }
-      }
-    }
+  // Configuration (R stacked tiles, BN, concat mode, phase groups).  tools/tune_tc2.py sweeps the whole space on
+  // hardware; across config-f 1024^2 (batch 2 and 8) and config-e 512^2 the winner only depends on Cout and on the
+  // layer kind -- widest N first (a 128 x N x 16 MMA fetches its 4 KB A tile from shared memory whatever N is, so
+  // small-N MMAs are operand-fetch bound), two accumulator stages where TMEM allows:
+  //     same-res:  Cout>=256 (1,256)   128 (2,128)   64 (2,64)   <=32 (4,Cout,concat)
+  //     up:        Cout>=256 (1,256, 2 groups)   128 (1,128, 2 groups)   64 (1,64)   <=32 (2,Cout)
+  // The search below (cost model) only decides when the preferred configuration is infeasible or leaves most SMs idle.
+  int best_r = 0, best_bn = 0, best_cat = 0, best_groups = 1;
+  static const int force_groups = [] { const char* e = getenv("MAUA_TC_GROUPS"); return e ? atoi(e) : 0; }();
+  // tools/tune_tc2.py: MAUA_TC_TUNE=1 makes every call read MAUA_TC_FORCE="R,BN,cat,groups"
+  static const bool tune = [] { const char* e = getenv("MAUA_TC_TUNE"); return e && e[0] == '1'; }();
+  int f_r = 0, f_bn = 0, f_cat = 0, f_groups = 0;
+  if (tune) {
+    const char* f = getenv("MAUA_TC_FORCE");
+    if (f && sscanf(f, "%d,%d,%d,%d", &f_r, &f_bn, &f_cat, &f_groups) != 4) f_r = 0;
   }
-  if (best_r == 0) return MAUA_E_UNSUPPORTED;
+  auto n_ctas = [&](int r, int bn, int groups) {
+    return tiles_x * ceil_div(rows16, (long long)r) * batch * (cout / bn) * groups;
+  };
+  auto feasible = [&](int r, int bn, int cat, int groups) {
+    if (r > rows16 || cout % bn != 0 || bn < 16 || bn > 256 || (bn & (bn - 1)) != 0) return false;
+    if (ep.rgb_out && bn != cout) return false;  // fused ToRGB needs every output channel in one CTA
+    if (cat && (n_products == 1 || bn > 64)) return false;
+    if (!up && groups != 1) return false;
+    const int blk = cat ? 2 * bn : bn;  // concat mode doubles the accumulator width
+    if (r * blk * (nphase / groups) > tmem_cap) return false;
+    const uint32_t plane = align1k((uint32_t)((TH * r + (up ? 1 : 2)) * (up ? TW + 1 : TW + 2) * kc * 2));
+    const uint32_t b_st = 2u * bn * kc * 2u;
+    return 2 * plane + 4 * b_st <= budget;  // A halo (hi+lo) + a B ring deep enough to hide TMA latency
+  };
+  auto search = [&]() {
+    double best_cost = 1e30;
+    long long best_ctas = 0;
+    for (int groups = 1; groups <= (up ? 4 : 1); groups <<= 1) {
+      if (up && force_groups && groups != force_groups) continue;
+      const int nph_item = nphase / groups;  // accumulator phases held by one work item
+      for (int r = 4; r >= 1; r >>= 1)
+        for (int bn = 256; bn >= 16; bn >>= 1)
+          for (int cat = 0; cat <= 1; ++cat) {
+            if (!feasible(r, bn, cat, groups)) continue;
+            const int blk = cat ? 2 * bn : bn;
+            const long long ctas = n_ctas(r, bn, groups);
+            // modelled tensor-pipe cycles per MMA of N columns: max(math N/2, operand fetch (4 KB A + 32N B) at
+            // ~115 B/clk); a single accumulator stage exposes the epilogue (penalty); L2->SMEM bytes per cycle as a
+            // secondary term (the halo is re-loaded once per phase group)
+            auto mma_cycles = [](double n) { const double f = (4096.0 + 32.0 * n) / 115.0; return n / 2.0 > f ? n / 2.0 : f; };
+            const double per_kstep = cat ? mma_cycles(2.0 * bn) + mma_cycles(bn) : (n_products > 1 ? 3.0 : 1.0) * mma_cycles(bn);
+            const double traffic = (groups * (TH * r + 2) * 10.0 / 9.0 + bn) / ((double)r * bn);
+            const double cost = per_kstep / bn * (2 * r * blk * nph_item <= 512 ? 1.0 : 1.2) + 0.15 * traffic;
+            const bool enough = ctas >= 120, best_enough = best_ctas >= 120;
+            const bool better = best_r == 0 || (enough && !best_enough) ||
+                                (enough == best_enough && (enough ? cost < best_cost : ctas > best_ctas));
+            if (better) { best_r = r; best_bn = bn; best_cat = cat; best_groups = groups; best_cost = cost; best_ctas = ctas; }
+          }
+    }
+  };
+  if (f_r) {
+    if (feasible(f_r, f_bn, f_cat, f_groups)) { best_r = f_r; best_bn = f_bn; best_cat = f_cat; best_groups = f_groups; }
+  } else {
+    int pr, pbn, pcat = 0, pg = 1;
+    if (cout >= 256) { pr = 1; pbn = 256; pg = up ? 2 : 1; }
+    else if (cout == 128) { pr = up ? 1 : 2; pbn = 128; pg = up ? 2 : 1; }
+    else if (cout == 64) { pr = up ? 1 : 2; pbn = 64; }
+    else { pr = up ? 2 : 4; pbn = cout; pcat = up ? 0 : 1; }
+    if (force_groups && up) pg = force_groups;
+    while (pr > 1 && pr > rows16) pr >>= 1;
+    // keep (most of) the 148 SMs busy: first fewer stacked tiles, then more phase groups, then narrower N
+    while (feasible(pr, pbn, pcat, pg) && n_ctas(pr, pbn, pg) < 120) {
+      if (pr > 1) pr >>= 1;
+      else if (up && pg < 4 && !force_groups) pg <<= 1;
+      else if (pbn > 64 && !ep.rgb_out) pbn >>= 1;
+      else break;
+    }
+    if (feasible(pr, pbn, pcat, pg)) { best_r = pr; best_bn = pbn; best_cat = pcat; best_groups = pg; }
+    else search();
+  }
+  const int unsupported = f_r ? MAUA_E_ARG : MAUA_E_UNSUPPORTED;  // a forced configuration must not fall back to v1
+  if (f_r) set_error("modconv_tc(v2): forced configuration %d,%d,%d,%d is infeasible", f_r, f_bn, f_cat, f_groups);
+  if (best_r == 0) return unsupported;
   const int R = best_r, bn = best_bn;
   p.R = R;
   p.BN = bn;
@@ -443,25 +506,26 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   p.a_plane = align1k((uint32_t)(p.HW_ * p.HH_ * kc * 2));
   p.cat = best_cat;
   const int blk_cols = p.cat ? 2 * bn : bn;
-  p.n_phase = nphase;
+  p.n_groups = best_groups;
+  p.n_phase = nphase / best_groups;
   int cols = 32;
   const uint32_t a_stage = 2 * p.a_plane, b_stage = 2u * bn * kc * 2u;
   p.SA = (2 * a_stage + 4 * b_stage <= budget) ? 2 : 1;
   int sb = (int)((budget - (uint32_t)p.SA * a_stage) / b_stage);
   // small layers: keep ALL weight tiles of the layer in shared memory for the lifetime of the persistent CTA
-  p.resident_b = (p.n_tiles == 1 && 9 * n_kchunks <= sb && 9 * n_kchunks <= 36) ? 1 : 0;
+  p.resident_b = (p.n_tiles == 1 && p.n_groups == 1 && 9 * n_kchunks <= sb && 9 * n_kchunks <= 36) ? 1 : 0;
   if (p.resident_b) sb = 9 * n_kchunks;
   else if (sb > 12) sb = 12;
-  if (sb < 2) return MAUA_E_UNSUPPORTED;
+  if (sb < 2) return unsupported;
   p.SB = sb;
   const size_t smem = (size_t)p.SA * a_stage + (size_t)p.SB * b_stage + 8 * (2 * p.SA + 2 * p.SB + 6) + 1024;
-  if (smem > 227 * 1024) return MAUA_E_UNSUPPORTED;
-  const long long items = tiles_x * p.tiles_y * batch * p.n_tiles;
+  if (smem > 227 * 1024) return unsupported;
+  const long long items = tiles_x * p.tiles_y * batch * p.n_tiles * p.n_groups;
   if (items >= (1LL << 31)) return MAUA_E_UNSUPPORTED;
   p.n_items = (int)items;
-  p.AS = (2 * blk_cols * R * nphase <= 512) ? 2 : 1;
+  p.AS = (2 * blk_cols * R * p.n_phase <= 512) ? 2 : 1;
   cols = 32;
-  while (cols < p.AS * blk_cols * R * nphase) cols <<= 1;
+  while (cols < p.AS * blk_cols * R * p.n_phase) cols <<= 1;
   p.tmem_cols = (uint32_t)cols;
   static int n_sm = 0;
   if (n_sm == 0) {
@@ -472,8 +536,8 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   const long long grid = items < n_sm ? items : n_sm;
   static const bool debug = [] { const char* e = getenv("MAUA_TC_DEBUG"); return e && e[0] == '1'; }();
   if (debug)
-    fprintf(stderr, "[modconv_tc2] %s B%d %d->%d @%dx%d: R=%d BN=%d cat=%d resB=%d AS=%d SA=%d SB=%d smem=%zuKB tmem=%u items=%lld grid=%lld\n",
-            up ? "up" : "same", batch, cin, cout, h, w, R, bn, p.cat, p.resident_b, p.AS, p.SA, p.SB, smem / 1024, p.tmem_cols, items, grid);
+    fprintf(stderr, "[modconv_tc2] %s B%d %d->%d @%dx%d: R=%d BN=%d cat=%d groups=%d resB=%d AS=%d SA=%d SB=%d smem=%zuKB tmem=%u items=%lld grid=%lld\n",
+            up ? "up" : "same", batch, cin, cout, h, w, R, bn, p.cat, p.n_groups, p.resident_b, p.AS, p.SA, p.SB, smem / 1024, p.tmem_cols, items, grid);
 
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   const auto swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
