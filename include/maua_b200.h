@@ -169,6 +169,10 @@ typedef struct MauaConvEpilogue {
    * rgb_out[b,k,y,x] = sum_c rgb_w[b,k,c] * act[b,c,y,x]  (no bias / skip: see maua_rgb_finish_f32).            */
   const float* rgb_w;        /* [B,3,Cout] = w_scale * Wrgb[k,c] * s_rgb[b,c] (maua_rgb_weights_f32) or NULL     */
   float* rgb_out;            /* [B,3,H,W] fp32                                                                    */
+  /* Optional scratch for the deterministic split-K of the tiny (<= 32^2) layers: ZERO-initialised once by the caller,
+   * restored to that state by every launch, private to one stream.  NULL (or too small) disables split-K.          */
+  void* workspace;
+  long long workspace_bytes;
 } MauaConvEpilogue;
 
 /* 3x3 modulated conv on the tensor cores.  x_hi/x_lo [B,H,W,Cin] bf16 (pre-scaled by s), w_hi/w_lo [9][Cout][Cin].

@@ -26,7 +26,7 @@ class ConvEpilogue(C.Structure):
                 ("s_next", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_f32_nchw", C.c_void_p),
                 ("out_raw_nhwc", C.c_void_p), ("noise_bstride", C.c_longlong), ("slope", C.c_float),
                 ("act_scale", C.c_float), ("activate", C.c_int32), ("reserved", C.c_int32), ("rgb_w", C.c_void_p),
-                ("rgb_out", C.c_void_p)]
+                ("rgb_out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong)]
 
 
 _p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong

@@ -48,7 +48,9 @@ __constant__ Step c_steps[2][9] = {
 struct Params {
   int B, H, W, Cin, Cout;  // input activation dims / channels
   int GH, GW;              // GEMM pixel grid: (H, W) or (H+1, W+1) for up
-  int TB, TH, TW;          // M tile = TB*TH*TW = 128
+  int TB, TH, TW;          // M tile = TB*TH*TW <= 128 rows (any factors: 17x7 covers the 17x17 grid of a 16^2 up layer)
+  int rows;                // TB*TH*TW: rows of the 128-row A tile the TMA box fills (the rest is never read back)
+  int S;                   // split-K: S CTAs share one output tile, each reduces n_kchunks/S K chunks
   int tiles_x, tiles_y;
   int BN, n_tiles;
   int n_kchunks;
@@ -86,8 +88,11 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- tile coordinates ------------------------------------------------------------------------------------------
-  const int n_tile = blockIdx.x % p.n_tiles;
-  const int m_tile = blockIdx.x / p.n_tiles;
+  const int split = blockIdx.x % p.S;
+  const int tile_id = blockIdx.x / p.S;
+  const int n_tile = tile_id % p.n_tiles;
+  const int m_tile = tile_id / p.n_tiles;
+  const int kc_per = p.n_kchunks / p.S, kc_begin = split * kc_per, kc_end = kc_begin + kc_per;
   const int tile_x = m_tile % p.tiles_x;
   const int tile_y = (m_tile / p.tiles_x) % p.tiles_y;
   const int tile_b = m_tile / (p.tiles_x * p.tiles_y);
@@ -123,14 +128,14 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const Step* steps = c_steps[UP ? 1 : 0];
-  const uint32_t a_bytes = (p.nprod > 1) ? A_STAGE : A_HALF;
+  const uint32_t a_bytes = (uint32_t)p.rows * ROW_BYTES * (p.nprod > 1 ? 2u : 1u);  // what the TMA boxes deliver
   const uint32_t b_bytes = (p.nprod > 1) ? b_stage : b_half;
 
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer ================================
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
-    for (int kc = 0; kc < p.n_kchunks; ++kc) {
+    for (int kc = kc_begin; kc < kc_end; ++kc) {
       const int c0 = kc * KC;
 #pragma unroll 1
       for (int st = 0; st < 9; ++st) {
@@ -160,7 +165,7 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     const uint64_t a_stage16 = A_STAGE >> 4, a_half16 = A_HALF >> 4, b_stage16 = b_stage >> 4, b_half16 = b_half >> 4;
     int ia = 0, ib = 0, cur_a = 0;
     uint32_t pa = 0, pb = 0, started = 0;
-    for (int kc = 0; kc < p.n_kchunks; ++kc) {
+    for (int kc = kc_begin; kc < kc_end; ++kc) {
 #pragma unroll 1
       for (int st = 0; st < 9; ++st) {
         const Step s = steps[st];
@@ -198,15 +203,49 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     const int m = quad * 32 + lane;
     const int tx = m % p.TW, ty = (m / p.TW) % p.TH, tb = m / (p.TW * p.TH);
     const int gx = x0 + tx, gy = y0 + ty, b = b0 + tb;
-    const bool in_grid = (b < p.B) && (gy < p.GH) && (gx < p.GW);
+    const bool in_grid = (m < p.rows) && (b < p.B) && (gy < p.GH) && (gx < p.GW);
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     constexpr int NPH = UP ? 4 : 1;
+    // ---- deterministic split-K: every CTA parks its partial accumulators in the workspace; the CTA that arrives last
+    // at the tile's counter sums the S partials in split order (so the result does not depend on which CTA that is)
+    // and runs the epilogue.  Layout: [4 KB counters][tile][split][16-column chunk][row m][16 floats] (coalesced).
+    const int n_chunks = NPH * p.BN / 16;
+    float* ws_tile = nullptr;
+    if (p.S > 1) {
+      ws_tile = reinterpret_cast<float*>(static_cast<char*>(ep.workspace) + 4096) +
+                (size_t)tile_id * p.S * n_chunks * 128 * 16;
+      float* mine = ws_tile + ((size_t)split * n_chunks * 128 + m) * 16;
+#pragma unroll 1
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        uint32_t r[16];
+        tmem_ld_x16(lane_addr + (uint32_t)(ch * 16), r);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(mine + (size_t)ch * 128 * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                               __uint_as_float(r[4 * i + 3]));
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      __shared__ int s_last;
+      if (threadIdx.x == 64) {
+        unsigned* counter = static_cast<unsigned*>(ep.workspace) + tile_id;
+        const unsigned old = atomicAdd(counter, 1u);
+        s_last = (old == (unsigned)p.S - 1u);
+        if (s_last) *counter = 0u;  // workspace is handed back zeroed (the next launch is stream-ordered)
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (!s_last) ws_tile = nullptr;
+      else __threadfence();
+    }
+    const bool do_epilogue = (p.S == 1) || (ws_tile != nullptr);
     const int bc = in_grid ? b : 0;
     const float* dptr = ep.d ? ep.d + (long long)bc * p.Cout + n0 : nullptr;
 #pragma unroll 1
-    for (int ph = 0; ph < NPH; ++ph) {
+    for (int ph = 0; ph < (do_epilogue ? NPH : 0); ++ph) {
       int oy, ox, OH, OW;
       bool valid;
       if (UP) {
@@ -222,15 +261,43 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         nz = __ldg(ep.noise_weight) * __ldg(ep.noise + (long long)b * ep.noise_bstride + (long long)oy * OW + ox);
 #pragma unroll 1
       for (int c = 0; c < p.BN; c += 16) {
-        uint32_t r[16];
-        tmem_ld_x16(lane_addr + (uint32_t)(ph * p.BN + c), r);
-        tmem_ld_wait();
-        if (!valid) continue;
         float v[16];
+        if (ws_tile) {
+          if (!valid) continue;
+          const float* src = ws_tile + ((size_t)((ph * p.BN + c) >> 4) * 128 + m) * 16;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          v[i] = __uint_as_float(r[i]);
-          if (dptr) v[i] *= __ldg(dptr + c + i);
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          const size_t sp_stride = (size_t)n_chunks * 128 * 16;
+#pragma unroll 1
+          for (int sp0 = 0; sp0 < p.S; sp0 += 4) {  // 4 partials in flight (L2 latency), summed in split order
+            float4 t[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (sp0 + j < p.S) {
+                const float4* q = reinterpret_cast<const float4*>(src + (size_t)(sp0 + j) * sp_stride);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) t[j][i] = __ldcg(q + i);
+              }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (sp0 + j < p.S) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  v[4 * i] += t[j][i].x; v[4 * i + 1] += t[j][i].y; v[4 * i + 2] += t[j][i].z; v[4 * i + 3] += t[j][i].w;
+                }
+              }
+          }
+        } else {
+          uint32_t r[16];
+          tmem_ld_x16(lane_addr + (uint32_t)(ph * p.BN + c), r);
+          tmem_ld_wait();
+          if (!valid) continue;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        }
+        if (dptr) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= __ldg(dptr + c + i);
         }
         if (UP) {
           float4* dst = reinterpret_cast<float4*>(ep.out_raw_nhwc + pix * p.Cout + n0 + c);
@@ -287,12 +354,6 @@ static int encode_bf16(CUtensorMap* m, const void* base, int rank, const cuuint6
                       row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
-static int next_pow2(int v) {
-  int p = 1;
-  while (p < v) p <<= 1;
-  return p;
-}
-
 }  // namespace tc
 }  // namespace maua
 
@@ -337,11 +398,26 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
   p.B = batch; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout;
   p.GH = up ? h + 1 : h;
   p.GW = up ? w + 1 : w;
-  p.TW = next_pow2(p.GW) < 16 ? next_pow2(p.GW) : 16;
-  int th = 128 / p.TW;
-  if (next_pow2(p.GH) < th) th = next_pow2(p.GH);
-  p.TH = th;
-  p.TB = 128 / (p.TW * p.TH);
+  // M tile: TB x TH x TW <= 128 pixels (one TMA box; factors need not be powers of two).  Whole images are folded
+  // over the batch while they fit; otherwise the (TW, TH) with the fewest tiles wins -- e.g. 17x7 / 11x11 cover the
+  // (H+1)^2 grids of the 16^2 / 32^2 up layers with 3 / 9 tiles per image instead of 6 / 15 for 16x8.
+  if (p.GW * p.GH <= 128) {
+    p.TW = p.GW; p.TH = p.GH;
+    p.TB = 128 / (p.GW * p.GH);
+    if (p.TB > batch) p.TB = batch;
+    const int nb = ceil_div(batch, p.TB);  // same tile count with a more even split (8 images: 5+3 -> 4+4)
+    p.TB = ceil_div(batch, nb);
+  } else {
+    p.TB = 1;
+    long long best = -1;
+    for (int tw = 1; tw <= 128 && tw <= p.GW; ++tw) {
+      int th = 128 / tw;
+      if (th > p.GH) th = p.GH;
+      const long long n = (long long)ceil_div(p.GW, tw) * ceil_div(p.GH, th);
+      if (best < 0 || n < best || (n == best && tw * th >= p.TW * p.TH)) { best = n; p.TW = tw; p.TH = th; }
+    }
+  }
+  p.rows = p.TW * p.TH * p.TB;
   p.tiles_x = ceil_div(p.GW, p.TW);
   p.tiles_y = ceil_div(p.GH, p.TH);
   const int tiles_b = ceil_div(batch, p.TB);
@@ -350,13 +426,37 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
   p.n_kchunks = cin / kc;
   p.nprod = n_products;
   const int nphase = up ? 4 : 1;
-  // N tile: largest power-of-two divisor of Cout that fits TMEM (512 columns over all phases); shrink while the
-  // grid would leave SMs idle (keeps at least 64 columns so the MMA stays reasonably efficient)
-  int bn = 16;
-  for (int c = 256; c >= 16; c >>= 1)
-    if (cout % c == 0 && c * nphase <= 512) { bn = c; break; }
-  while (bn > 64 && m_tiles * (cout / bn) < 148 && cout % (bn / 2) == 0) bn >>= 1;
+  // (BN, S): modelled cycles = waves * (per-CTA MMA time + fixed prologue/epilogue).  A wide N keeps the MMA efficient
+  // (every 128 x N x 16 MMA fetches 4 KB of A whatever N is); when that leaves SMs idle the K loop is split over S
+  // CTAs per tile (deterministic reduction through ep.workspace) instead of shrinking N.
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  }
+  static const int force_s = [] { const char* e = getenv("MAUA_TC_SPLITK"); return e ? atoi(e) : 0; }();
+  int bn = 16, best_s = 1;
+  double best_cost = 1e30;
+  for (int c = 256; c >= 16; c >>= 1) {
+    if (cout % c != 0 || c * nphase > 512) continue;
+    for (int sk = 1; sk <= p.n_kchunks && sk <= 16; sk <<= 1) {
+      if (p.n_kchunks % sk != 0) continue;
+      if (force_s && sk != force_s && !(force_s > p.n_kchunks && sk == 1)) continue;
+      const long long ctas = m_tiles * (cout / c) * sk;
+      if (sk > 1) {
+        const long long need = 4096 + m_tiles * (cout / c) * sk * (long long)(nphase * c) * 128 * 4;
+        if (!ep.workspace || need > ep.workspace_bytes || m_tiles * (cout / c) > 1024) continue;
+      }
+      const double fetch = (4096.0 + 32.0 * c) / 115.0, mma = (c / 2.0 > fetch ? c / 2.0 : fetch);
+      const double per_cta = 9.0 * (p.n_kchunks / sk) * (kc / 16) * (n_products > 1 ? 3 : 1) * mma + 6000.0 +
+                             (sk > 1 ? 4000.0 + 1000.0 * ((sk + 3) / 4) * (nphase * c / 16) : 0.0);  // reduce: L2 latency bound
+      const double cost = (double)ceil_div(ctas, (long long)n_sm) * per_cta;
+      if (cost < best_cost) { best_cost = cost; bn = c; best_s = sk; }
+    }
+  }
   p.BN = bn;
+  p.S = best_s;
   p.n_tiles = cout / bn;
   int cols = 32;
   while (cols < bn * nphase) cols <<= 1;
@@ -370,9 +470,14 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
   if (stages < 2) stages = 2;
   p.SA = stages;
   p.SB = stages;
+  static const bool debug = [] { const char* e = getenv("MAUA_TC_DEBUG"); return e && e[0] == '1'; }();
+  if (debug)
+    fprintf(stderr, "[modconv_tc v1] %s B%d %d->%d @%dx%d: tile %dx%dx%d (%d rows) m_tiles=%lld BN=%d S=%d stages=%d grid=%lld\n",
+            up ? "up" : "same", batch, cin, cout, h, w, p.TB, p.TH, p.TW, p.rows, m_tiles, bn, p.S, stages,
+            m_tiles * p.n_tiles * p.S);
   const size_t smem = (size_t)stages * (a_stage + b_stage) + 8 * (2 * p.SA + 2 * p.SB + 2) + 1024;
   MAUA_CHECK_ARG(smem <= 227 * 1024, "modconv_tc: shared memory budget exceeded");
-  MAUA_CHECK_ARG(m_tiles * p.n_tiles < (1LL << 31), "modconv_tc: grid too large");
+  MAUA_CHECK_ARG(m_tiles * p.n_tiles * p.S < (1LL << 31), "modconv_tc: grid too large");
 
   // tensor maps: activations [B,H,W,Cin] (dims innermost first), weights [9][Cout][Cin]
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
@@ -394,7 +499,7 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
   }
 
   cudaStream_t st = as_stream(stream);
-  const unsigned grid = (unsigned)(m_tiles * p.n_tiles);
+  const unsigned grid = (unsigned)(m_tiles * p.n_tiles * p.S);
 #define MAUA_TC_LAUNCH(KCV, UPV)                                                                                   \
   do {                                                                                                             \
     static size_t smem_set = 0; /* per instantiation; never called again during CUDA-graph capture */            \

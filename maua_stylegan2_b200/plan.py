@@ -13,6 +13,9 @@ import torch
 from . import _lib as L
 
 
+SPLITK_WORKSPACE_BYTES = 64 << 20
+
+
 class LayerPlan:
     __slots__ = ("spec", "job", "rgb_job", "wsq", "w_hi", "w_lo", "s_off", "d_off", "rgb_s_off", "tc_ok")
 
@@ -62,8 +65,11 @@ def build_plan(g, key):
             lp.rgb_s_off = s_total
             s_total += sp.rgb.conv.in_channel
         layers.append(lp)
+    # scratch of the deterministic split-K (tiny layers): zeroed once, every launch hands it back zeroed; launches that
+    # share it must be stream-ordered (one Generator forward at a time per device -- the frame loop's single compute stream)
+    workspace = torch.zeros(SPLITK_WORKSPACE_BYTES, device=device, dtype=torch.uint8) if g.impl == "tc" else None
     return {"key": key, "layers": layers, "s_total": s_total, "d_total": d_total, "n_jobs": n_jobs,
-            "device": device, "batch": {}}
+            "device": device, "batch": {}, "workspace": workspace}
 
 
 def batch_buffers(g, plan, batch):

@@ -61,37 +61,60 @@ class FramePipeline:
         self._graphs = [None, None]
         self._slot_busy = [None, None]  # per ping-pong slot: (d2h-done event, collective work) still reading its frames
 
-    def _graph_step(self, n, slot):
-        """Copy batch n into the slot's static inputs and replay its captured forward; returns the static uint8 frames."""
+    def _graph_slot(self, slot, n):
+        """Static inputs + captured forward of one ping-pong slot (created on first use: one eager run, then capture)."""
+        gs = self._graphs[slot]
+        if gs is not None:
+            return gs
         sl = slice(n, n + self.batch)
+        gs = {"latent": torch.empty((self.batch,) + tuple(self.latents.shape[1:]), device=self.device),
+              "noise": [None if ns is None else (ns.to(self.device) if ns.shape[0] == 1 else
+                                                 torch.empty((self.batch,) + tuple(ns.shape[1:]), device=self.device))
+                        for ns in self.noise],
+              "trunc": self.truncation if isinstance(self.truncation, float) else
+              torch.empty(self.batch, device=self.device),
+              "ready": None, "consumed": None}
+        self._graphs[slot] = gs
+        self._fill_static(gs, sl)
+        run = lambda: self.g(styles=gs["latent"], noise=gs["noise"], truncation=gs["trunc"], transform_dict_list=[],
+                             randomize_noise=False, input_is_latent=True, return_u8=True)[0]
+        run()
+        torch.cuda.current_stream(self.device).synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            gs["out"] = run()
+        gs["graph"] = graph
+        return gs
+
+    def _graph_prefetch(self, n, slot):
+        """H2D of batch n into the slot's static inputs on the COPY stream: it overlaps the other slot's replay and only
+        waits for this slot's previous replay (which read the same buffers)."""
+        gs = self._graph_slot(slot, n)
+        with torch.cuda.stream(self.copy_stream):
+            if gs["consumed"] is not None:
+                self.copy_stream.wait_event(gs["consumed"])
+            self._fill_static(gs, slice(n, n + self.batch))
+            gs["ready"] = torch.cuda.Event()
+            gs["ready"].record(self.copy_stream)
+
+    def _graph_step(self, n, slot):
+        """Replay the slot's captured forward on batch n (prefetched, or copied now); returns the static uint8 frames."""
+        cur = torch.cuda.current_stream(self.device)
         busy = self._slot_busy[slot]
         if busy is not None:  # the static output of this slot may still be read by the D2H copy / all-gather of step i-2
             if busy[0] is not None:
-                torch.cuda.current_stream(self.device).wait_event(busy[0])
+                cur.wait_event(busy[0])
             if busy[1] is not None:
                 busy[1].wait()
             self._slot_busy[slot] = None
-        gs = self._graphs[slot]
-        if gs is None:
-            # static inputs, one eager warm-up (plan / attribute setup happens here), then capture
-            gs = {"latent": torch.empty((self.batch,) + tuple(self.latents.shape[1:]), device=self.device),
-                  "noise": [None if ns is None else (ns.to(self.device) if ns.shape[0] == 1 else
-                                                     torch.empty((self.batch,) + tuple(ns.shape[1:]), device=self.device))
-                            for ns in self.noise],
-                  "trunc": self.truncation if isinstance(self.truncation, float) else
-                  torch.empty(self.batch, device=self.device)}
-            self._graphs[slot] = gs
-            self._fill_static(gs, sl)
-            run = lambda: self.g(styles=gs["latent"], noise=gs["noise"], truncation=gs["trunc"], transform_dict_list=[],
-                                 randomize_noise=False, input_is_latent=True, return_u8=True)[0]
-            run()
-            torch.cuda.current_stream(self.device).synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                gs["out"] = run()
-            gs["graph"] = graph
-        self._fill_static(gs, sl)
+        gs = self._graph_slot(slot, n)
+        if gs["ready"] is None:
+            self._graph_prefetch(n, slot)
+        cur.wait_event(gs["ready"])
+        gs["ready"] = None
         gs["graph"].replay()
+        gs["consumed"] = torch.cuda.Event()
+        gs["consumed"].record(cur)
         return gs["out"]
 
     def warmup(self):
@@ -212,6 +235,8 @@ class FramePipeline:
             full = n + self.batch <= self.n_frames
             if graph_ok and full:
                 frames = self._graph_step(n, i & 1)
+                if i + 1 < steps and batch_start(i + 1) + self.batch <= self.n_frames:
+                    self._graph_prefetch(batch_start(i + 1), (i + 1) & 1)   # overlaps this step's replay
             else:
                 item = nxt if nxt is not None else self._stage(n)
                 nxt = self._stage(batch_start(i + 1)) if (i + 1 < steps and not graph_ok) else None

@@ -123,6 +123,8 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
                 ep.out_hi, ep.out_lo = L.ptr(o_hi), L.ptr(o_lo)
                 ep.out_f32_nchw = L.ptr(y)
                 ep.slope, ep.act_scale, ep.activate = 0.2, SQRT2, 1
+                ws = plan["workspace"]
+                ep.workspace, ep.workspace_bytes = L.ptr(ws), (ws.numel() if ws is not None else 0)
                 rgb_partial = None
                 if fuse_rgb:
                     rs_f, _ = bc["views"][lp.rgb_job]
@@ -139,6 +141,7 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
                     u = torch.empty((batch, 2 * in_h + 1, 2 * in_w + 1, sp.cout), device=device, dtype=torch.float32)
                     ep_raw = L.ConvEpilogue()
                     ep_raw.d, ep_raw.out_raw_nhwc, ep_raw.activate = d.data_ptr(), u.data_ptr(), 0
+                    ep_raw.workspace, ep_raw.workspace_bytes = ep.workspace, ep.workspace_bytes
                     L.call("maua_modconv_tc", split[0].data_ptr(), split[1].data_ptr(), lp.w_hi.data_ptr(),
                            lp.w_lo.data_ptr(), C.byref(ep_raw), batch, sp.cin, sp.cout, in_h, in_w, 1, nprod, stream)
                     L.call("maua_blur_act_nhwc", u.data_ptr(), conv.blur.kernel.data_ptr(), C.byref(ep), batch, sp.cout,

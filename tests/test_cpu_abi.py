@@ -42,7 +42,7 @@ def test_struct_layouts_match_c():
     from maua_stylegan2_b200 import _lib as L
 
     assert ctypes.sizeof(L.StyleJob) == 56
-    assert ctypes.sizeof(L.ConvEpilogue) == 112
+    assert ctypes.sizeof(L.ConvEpilogue) == 128
 
 
 def test_cpu_tensors_fail_loudly():

@@ -19,7 +19,7 @@ def _pack(w, scale):
     return _pack_tc(w[None].contiguous(), scale)
 
 
-def _run_tc(x, w, s, d, noise, nw, bias, s_next, up, nprod, scale):
+def _run_tc(x, w, s, d, noise, nw, bias, s_next, up, nprod, scale, workspace=None):
     from maua_stylegan2_b200 import _lib as L
     from maua_stylegan2_b200.synthesis import _modulate_split
 
@@ -38,6 +38,8 @@ def _run_tc(x, w, s, d, noise, nw, bias, s_next, up, nprod, scale):
     ep.bias, ep.s_next = bias.data_ptr(), s_next.data_ptr()
     ep.out_hi, ep.out_lo, ep.out_f32_nchw = o_hi.data_ptr(), o_lo.data_ptr(), y.data_ptr()
     ep.slope, ep.act_scale, ep.activate = 0.2, 2 ** 0.5, 1
+    if workspace is not None:
+        ep.workspace, ep.workspace_bytes = workspace.data_ptr(), workspace.numel()
     u = None
     if not up:
         ep.d = d.data_ptr()
@@ -47,6 +49,7 @@ def _run_tc(x, w, s, d, noise, nw, bias, s_next, up, nprod, scale):
         u = torch.full((b, 2 * h + 1, 2 * wd + 1, cout), float("nan"), device="cuda")
         er = L.ConvEpilogue()
         er.d, er.out_raw_nhwc, er.activate = d.data_ptr(), u.data_ptr(), 0
+        er.workspace, er.workspace_bytes = ep.workspace, ep.workspace_bytes
         L.call("maua_modconv_tc", hi.data_ptr(), lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), C.byref(er), b, cin,
                cout, h, wd, 1, nprod, stream)
         k = torch.tensor([1.0, 3.0, 3.0, 1.0])
@@ -86,6 +89,9 @@ CASES = [
     (8, 512, 512, 4, 4, True),
     (1, 64, 32, 32, 32, True),       # KC=64, BN=32, 4 phases
     (2, 32, 16, 9, 7, True),         # odd sizes
+    (8, 512, 512, 16, 16, True),     # 17x17 grid -> 17x7 tiles (TMA box with fewer than 128 rows)
+    (4, 256, 256, 32, 32, True),     # 33x33 grid -> 11x11 tiles
+    (3, 64, 64, 5, 3, True),         # whole images folded over the batch, ragged last tile
 ]
 
 
@@ -104,6 +110,19 @@ def test_tc_conv_matches_fp64_reference(b, cin, cout, h, w, up):
     scale = 1 / (cin * 9) ** 0.5
     ref, raw = _reference(x, wt, s, d, noise, nw, bias, up, scale)
     y, o_hi, o_lo, u = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 3, scale)
+    _check(ref, raw, y, o_hi, o_lo, u, s_next, up)
+    # same layer with the split-K scratch available: identical maths, S partial sums reduced in a fixed order
+    ws = torch.zeros(64 << 20, device="cuda", dtype=torch.uint8)
+    y2, o_hi2, o_lo2, u2 = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 3, scale, workspace=ws)
+    _check(ref, raw, y2, o_hi2, o_lo2, u2, s_next, up)
+    assert not ws[:4096].any(), "split-K must hand the tile counters back zeroed"
+    y3, _, _, u3 = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 3, scale, workspace=ws)
+    assert torch.equal(y2, y3), "split-K reduction must be bitwise reproducible"
+    if up:
+        assert torch.equal(u2, u3)
+
+
+def _check(ref, raw, y, o_hi, o_lo, u, s_next, up):
     if up:
         assert rel_err(u.cpu().numpy(), raw.numpy()) < 2e-4, "raw transposed-conv phases"
     assert not torch.isnan(y).any()
