@@ -53,14 +53,15 @@ struct Params {
 // the four sub-pixel phases (py,px) accumulate side by side in TMEM and share the one halo load.
 struct Tap { int8_t hy, hx, tap, phase; };  // phase = accumulator index LOCAL to the work item
 struct TapList { int32_t n; Tap t[9]; };
-// [0] same-res; transposed: [1] all four phases in one item; [2..3] two phase groups {0,1} / {2,3};
-// [4..7] one phase per item.  Phase splitting trades extra halo loads (cheap) for fewer accumulator columns per item,
-// i.e. room for two accumulator stages (epilogue overlap) and/or a wider N tile.
+// [0] same-res; transposed: [1] all four phases in one item; [2..3] two phase groups {0,3} / {1,2} (5 + 4 taps: the
+// most even split of the 4+2+2+1 taps); [4..7] one phase per item.  Phase splitting trades extra halo loads (cheap) for
+// fewer accumulator columns per item, i.e. room for two accumulator stages (epilogue overlap) and/or a wider N tile.
+// Items are ordered group-slowest, so every persistent CTA walks the same mix of heavy and light groups.
 __constant__ TapList c_taps[8] = {
     {9, {{0, 0, 0, 0}, {0, 1, 1, 0}, {0, 2, 2, 0}, {1, 0, 3, 0}, {1, 1, 4, 0}, {1, 2, 5, 0}, {2, 0, 6, 0}, {2, 1, 7, 0}, {2, 2, 8, 0}}},
     {9, {{1, 1, 0, 0}, {1, 1, 1, 1}, {1, 0, 2, 0}, {1, 1, 3, 2}, {1, 1, 4, 3}, {1, 0, 5, 2}, {0, 1, 6, 0}, {0, 1, 7, 1}, {0, 0, 8, 0}}},
-    {6, {{1, 1, 0, 0}, {1, 0, 2, 0}, {0, 1, 6, 0}, {0, 0, 8, 0}, {1, 1, 1, 1}, {0, 1, 7, 1}}},  // phases 0,1
-    {3, {{1, 1, 3, 0}, {1, 0, 5, 0}, {1, 1, 4, 1}}},                                            // phases 2,3
+    {5, {{1, 1, 0, 0}, {1, 0, 2, 0}, {0, 1, 6, 0}, {0, 0, 8, 0}, {1, 1, 4, 1}}},                // phases 0,3
+    {4, {{1, 1, 1, 0}, {0, 1, 7, 0}, {1, 1, 3, 1}, {1, 0, 5, 1}}},                              // phases 1,2
     {4, {{1, 1, 0, 0}, {1, 0, 2, 0}, {0, 1, 6, 0}, {0, 0, 8, 0}}},                              // phase 0
     {2, {{1, 1, 1, 0}, {0, 1, 7, 0}}},                                                          // phase 1
     {2, {{1, 1, 3, 0}, {1, 0, 5, 0}}},                                                          // phase 2
@@ -111,13 +112,14 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // work item -> (n tile, phase group, pixel tile); n fastest, then group: concurrently running CTAs share the halo
-  // through L2
+  // work item -> (phase group, pixel tile, n tile); n fastest (concurrently running CTAs share the halo through L2),
+  // group slowest (load balance: the groups have 5/4 or 4/2/2/1 taps)
   auto decode = [&](int item, int& n0, int& grp, int& x0, int& y0, int& b) {
+    const int per_group = p.n_items / p.n_groups;
+    grp = item / per_group;
+    item -= grp * per_group;
     const int n_tile = item % p.n_tiles;
-    int rest = item / p.n_tiles;
-    grp = rest % p.n_groups;
-    rest /= p.n_groups;
+    const int rest = item / p.n_tiles;
     x0 = (rest % p.tiles_x) * TW;
     y0 = ((rest / p.tiles_x) % p.tiles_y) * TH * p.R;
     b = rest / (p.tiles_x * p.tiles_y);
@@ -259,7 +261,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const bool in_grid = (gy < p.GH) && (gx < p.GW);
 #pragma unroll 1
         for (int ph = 0; ph < p.n_phase; ++ph) {
-        const int gph = UP ? grp * p.n_phase + ph : 0;  // global sub-pixel phase (py, px) = (gph >> 1, gph & 1)
+        // global sub-pixel phase (py, px) = (gph >> 1, gph & 1); two groups hold phases {0,3} and {1,2}
+        const int gph = !UP ? 0 : (p.n_groups == 2 ? (grp == 0 ? 3 * ph : 1 + ph) : grp * p.n_phase + ph);
         int oy, ox, OH, OW;
         bool valid;
         if (UP) {
@@ -419,7 +422,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   // layer kind -- widest N first (a 128 x N x 16 MMA fetches its 4 KB A tile from shared memory whatever N is, so
   // small-N MMAs are operand-fetch bound), two accumulator stages where TMEM allows:
   //     same-res:  Cout>=256 (1,256)   128 (2,128)   64 (2,64)   <=32 (4,Cout,concat)
-  //     up:        Cout>=256 (1,256, 2 groups)   128 (1,128, 2 groups)   64 (1,64)   <=32 (2,Cout)
+  //     up:        Cout>=256 (1,256, 4 groups)   128 (1,128, 2 groups)   64 (2,64, 2 groups)   <=32 (2,Cout)
   // The search below (cost model) only decides when the preferred configuration is infeasible or leaves most SMs idle.
   int best_r = 0, best_bn = 0, best_cat = 0, best_groups = 1;
   static const int force_groups = [] { const char* e = getenv("MAUA_TC_GROUPS"); return e ? atoi(e) : 0; }();
@@ -474,9 +477,9 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     if (feasible(f_r, f_bn, f_cat, f_groups)) { best_r = f_r; best_bn = f_bn; best_cat = f_cat; best_groups = f_groups; }
   } else {
     int pr, pbn, pcat = 0, pg = 1;
-    if (cout >= 256) { pr = 1; pbn = 256; pg = up ? 2 : 1; }
+    if (cout >= 256) { pr = 1; pbn = 256; pg = up ? 4 : 1; }
     else if (cout == 128) { pr = up ? 1 : 2; pbn = 128; pg = up ? 2 : 1; }
-    else if (cout == 64) { pr = up ? 1 : 2; pbn = 64; }
+    else if (cout == 64) { pr = 2; pbn = 64; pg = up ? 2 : 1; }
     else { pr = up ? 2 : 4; pbn = cout; pcat = up ? 0 : 1; }
     if (force_groups && up) pg = force_groups;
     while (pr > 1 && pr > rows16) pr >>= 1;
