@@ -46,6 +46,20 @@ def peaks():
     return p
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch set of `kernel`, from the newest committed
+    `ncu --set full` capture of this same step (profiles/rNN_traffic.json, written by tools/collect_profiles.py)."""
+    d = os.path.join(ROOT, "profiles")
+    try:
+        for f in sorted((x for x in os.listdir(d) if x.endswith("_traffic.json")), reverse=True):
+            t = json.load(open(os.path.join(d, f)))
+            if kernel in t:
+                return t[kernel]["dram_bytes"]
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # workload (synthetic, shape-faithful to audioreactive/examples/default.py)
 # ----------------------------------------------------------------------------------------------------------------
@@ -376,7 +390,9 @@ def main():
                 nprod = 3 if (args.precision == "bf16x3" and args.conv == "tc") else 1
                 roof = {"kernel": "maua_modconv_tc" if args.conv == "tc" else "maua_modconv_simt_f32", "bound": "tensor",
                         "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " sustained bf16",
+                        "frac": ach / pk["bf16_tflops_sustained"], "traffic": ncu_traffic("maua_modconv_tc") if args.conv == "tc" and B == 8 else None,
+                        "traffic_unit": "bytes of DRAM read+write per launch set (17 conv launches of one batch-8 step), ncu",
+                        "peak_source": pk["source"] + " sustained bf16",
                         "algorithmic_gflop_per_launch_set": conv_fl / nprof / 1e9,
                         "products_per_mac": nprod, "issued_frac": nprod * ach / pk["bf16_tflops_sustained"],
                         "ms_per_step": conv_ms / nprof,
@@ -401,7 +417,8 @@ def main():
             by = 4.0 * (x.numel() + y.numel())
             gbs = by / (s.elapsed_time(e) / reps * 1e-3) / 1e9
             roof_ufd = {"kernel": "maua_upfirdn2d_f32 (blur_tile)", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
-                        "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None,
+                        "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": ncu_traffic("maua_upfirdn2d_f32") if bb == 4 else None,
+                        "algorithmic_bytes": by,
                         "shape": f"[{bb},32,2049,2049]->[{bb},32,2048,2048] fp32 (in+out {by / 1e9:.2f} GB > L2)"}
             del x, y
 

@@ -26,6 +26,8 @@
  *   maua_noise_bias_act_f32   <- NoiseInjection.forward + FusedLeakyReLU.forward models/stylegan2.py:262-266, op/fused_act.py:82-97
  *   maua_torgb_f32            <- ToRGB.forward (1x1 modconv + bias + Upsample(skip))      models/stylegan2.py:356-365
  *   maua_rgb_to_u8_nhwc       <- render.split_batches clamp/scale/permute/astype(uint8)   render.py:40-43
+ *   maua_bend_warp_f32        <- Translate / Zoom / Rotate network bends                  audioreactive/bend.py:51-102
+ *   maua_perlin_noise         <- perlin_noise                                             audioreactive/latent.py:188-246
  */
 #ifndef MAUA_B200_H
 #define MAUA_B200_H
@@ -238,6 +240,25 @@ int maua_chroma_weight_latents_f32(const float* chroma, const float* selection, 
 /* examples/default.py:20-21: x[t][e] = envelope[t]*target[e] + (1 - envelope[t])*x[t][e] */
 int maua_envelope_blend_f32(float* x, const float* envelope, const float* target, int n_frames, long long inner,
                             void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Network bending + looping noise
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* audioreactive/bend.py:51-102 (Translate / Zoom / Rotate) as one kernel:
+ *   P   = pad_stages(x) (+ noise)            pad_*_host: n_pad_* (left, right) pairs applied in order, HOST ints;
+ *                                            pad_mode 0 = nn.ReflectionPad2d, 1 = nn.ReplicationPad2d
+ *   y[b,c,oy,ox] = bilinear_zeros(P[b,c], M_b^-1 (ox + crop_x0, oy + crop_y0))
+ * x: [B,C,H,W]; y: [B,C,out_h,out_w]; noise (may be NULL): [noise_b,noise_c,Hp,Wp] with noise_b in {1,B},
+ * noise_c in {1,C} (AddNoise, bend.py:28-40); minv: [B,6] row-major 2x3 INVERSE affine (padded-frame pixels,
+ * x first): sx = m0*X + m1*Y + m2, sy = m3*X + m4*Y + m5  (kornia warp_affine, bilinear, zeros, align_corners). */
+int maua_bend_warp_f32(const float* x, float* y, const float* noise, const float* minv, int batch, int ch, int h, int w,
+                       const int* pad_x_host, int n_pad_x, const int* pad_y_host, int n_pad_y, int pad_mode,
+                       int noise_b, int noise_c, int out_h, int out_w, int crop_y0, int crop_x0, void* stream);
+/* audioreactive/latent.py:188-246 perlin_noise: gradients [r0+1,r1+1,r2+1,3] fp64 (tileable wrap already applied),
+ * out [s0,s1,s2] fp64 (out_f64 != 0) or fp32; s_i % r_i == 0; values in [-1, 1] after the reference's `*2 - 1`. */
+int maua_perlin_noise(const double* gradients, void* out, int s0, int s1, int s2, int r0, int r1, int r2, int out_f64,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -2,7 +2,7 @@
 
 Run once in the build container (the reference cannot travel to the GPU box):
     python tests/golden/make_golden.py
-Writes tests/golden/{ops_golden,generator_g32,generator_g128,audio_glue}.npz.  Inputs are derived from
+Writes tests/golden/{ops_golden,generator_g32,generator_g128,audio_glue}.npz (`--plugins`: only plugins.npz).  Inputs are derived from
 numpy PCG64 seeds (oracle.stylegan2_oracle.synth_state_dict), so the fixtures only store the reference's OUTPUTS
 (images + strided samples of the activation maps) and small inputs.
 
@@ -165,8 +165,44 @@ def audio_glue_cases(ar):
     return out
 
 
+def plugin_cases(ar):
+    """audioreactive/latent.py functions the example hook files call: perlin_noise
+    (its `.cuda()` calls are made a no-op for this CPU run; the arithmetic is untouched), spline_loops, slerp."""
+    out = {}
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for name, shape, res, tile in (("a", (12, 8, 16), (3, 2, 4), (True, False, False)),
+                                       ("b", (16, 32, 32), (1, 1, 1), (True, False, False)),
+                                       ("c", (24, 16, 8), (8, 4, 4), (True, True, False)),
+                                       ("d", (10, 6, 9), (5, 3, 3), (False, False, True))):
+            np.random.seed(100 + ord(name))
+            y = ar.perlin_noise(shape=shape, res=res, tileable=tile)
+            out[f"perlin_{name}_cfg"] = np.array(list(shape) + list(res) + [int(t) for t in tile] + [100 + ord(name)])
+            out[f"perlin_{name}_y"] = y.numpy()
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    rng = np.random.Generator(np.random.PCG64(21))
+    sel = rng.standard_normal((4, 6, 32)).astype(np.float32)
+    out["spline_sel"] = sel
+    out["spline_y_100_2"] = ar.spline_loops(sel, 100, 2).numpy()
+    out["spline_y_97_3_noloop"] = ar.spline_loops(sel, 97, 3, loop=False).numpy()
+    out["spline_y_64_half"] = ar.spline_loops(sel, 64, 0.5).numpy()      # kelp.py passes fractional n_loops
+    a, b = rng.standard_normal(32), rng.standard_normal(32)
+    out["slerp_a"], out["slerp_b"] = a, b
+    out["slerp_y"] = np.stack([ar.slerp(v, a, b) for v in (0.0, 0.25, 0.5, 1.0)])
+    out["slerp_same"] = ar.slerp(0.3, a, a)
+    t = torch.arange(10)
+    out["wrap_8_5"] = ar.wrapping_slice(t, 8, 5).numpy()
+    out["wrap_2_4"] = ar.wrapping_slice(t, 2, 4).numpy()
+    return out
+
+
 def main():
     op, ref_sg2, ar = import_reference()
+    if "--plugins" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "plugins.npz"), **plugin_cases(ar))
+        return
     torch.set_grad_enabled(False)
     np.savez_compressed(os.path.join(HERE, "ops_golden.npz"), **ops_cases(op))
     np.savez_compressed(os.path.join(HERE, "generator_g32.npz"), **gen_case(ref_sg2, 32, 2, 2, seed=3, psi_lo=0.5))
