@@ -71,8 +71,11 @@ int maua_fused_bias_act_f32(const float* x, const float* b, const float* ref, fl
  * Style / mapping
  * ---------------------------------------------------------------------------------------------------------- */
 
-/* y[b,n] = act( sum_k x[b,k] * w[n,k] * w_scale + bias[n] * bias_scale );  act 0: none, 1: lrelu(0.2)*sqrt(2).
- * pixel_norm != 0 first normalises each row of x: x * rsqrt(mean(x^2) + 1e-8) (models/stylegan2.py:15-20). */
+/* y[b,n] = act( sum_k x[b,k] * w[n,k] * w_scale + bias[n] * bias_scale );  act 0: none, 1: lrelu(0.2)*sqrt(2),
+ * act 2: as 1 but bias[0] for every n — what the reference CUDA op computes for the 3-D [1,1,N] tensors of
+ * `Generator(map_latents=True)` (models/stylegan2.py:506-509, op/fused_bias_act_kernel.cu:29,67-69).
+ * pixel_norm 1 first normalises each row of x: x * rsqrt(mean(x^2) + 1e-8) (models/stylegan2.py:15-20);
+ * pixel_norm 2 normalises each ELEMENT by itself (the same module over the singleton axis of [1,1,N]). */
 int maua_linear_f32(const float* x, const float* w, const float* bias, float* y, int batch, int in_dim, int out_dim,
                     float w_scale, float bias_scale, int act, int pixel_norm, void* stream);
 

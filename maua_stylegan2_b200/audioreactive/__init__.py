@@ -1,4 +1,5 @@
 """Device-side drop-in for the reference's `audioreactive` package (signal + latent halves)."""
+from .bend import *  # noqa: F401,F403
 from .latent import *  # noqa: F401,F403
 from .signal import *  # noqa: F401,F403
 from . import signal as _signal

@@ -124,7 +124,16 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
     sq = fmaf(v, v, sq);
   }
   float norm = 1.f;
-  if (pixel_norm) {
+  if (pixel_norm == 2) {
+    // PixelNorm over a SINGLETON axis (reference map_latents path feeds [1,1,512]: models/stylegan2.py:20,507):
+    // every element is normalised by itself, x * rsqrt(x^2 + 1e-8)
+    __syncthreads();
+    for (int i = tid; i < in_dim; i += 256) {
+      const float v = sx[i];
+      sx[i] = v * rsqrtf(v * v + 1e-8f);
+    }
+    __syncthreads();
+  } else if (pixel_norm) {
     sq = warp_sum(sq);
     if (lane == 0) red[warp] = sq;
     __syncthreads();
@@ -143,8 +152,10 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
   acc = warp_sum(acc);
   if (lane == 0) {
     float v = acc * w_scale;
-    if (bias) v += __ldg(bias + n) * bias_scale;
-    if (act == 1) v = (v > 0.f ? v : v * 0.2f) * 1.4142135623730951f;
+    // act 2: the reference CUDA op on a 3-D [1,1,N] input indexes bias[(i / step_b) % size_b] with step_b = N, i.e.
+    // bias[0] for every feature (op/fused_bias_act_kernel.cu:29,67-69)
+    if (bias) v += __ldg(bias + (act == 2 ? 0 : n)) * bias_scale;
+    if (act >= 1) v = (v > 0.f ? v : v * 0.2f) * 1.4142135623730951f;
     y[(long long)b * out_dim + n] = v;
   }
 }

@@ -104,10 +104,10 @@ class EqualLinear(nn.Module):
         self.scale = (1 / math.sqrt(in_dim)) * lr_mul
         self.lr_mul = lr_mul
 
-    def forward(self, inputs, pixel_norm=False):
+    def forward(self, inputs, pixel_norm=False, bias0=False):
         lead = inputs.shape[:-1]
         out = _linear(inputs.reshape(-1, inputs.shape[-1]), self.weight, self.bias, self.scale, self.lr_mul,
-                      1 if self.activation else 0, pixel_norm)
+                      (2 if bias0 else 1) if self.activation else 0, pixel_norm)
         return out.view(*lead, -1)
 
     def __repr__(self):
@@ -434,14 +434,17 @@ class Generator(nn.Module):
         latent_in = torch.randn(n_latent, self.style_dim, device=self.input.input.device)
         return self.get_latent(latent_in).mean(0, keepdim=True)
 
-    def get_latent(self, inputs):
-        """Mapping network on [N, style_dim] (PixelNorm fused into the first EqualLinear launch)."""
+    def get_latent(self, inputs, reference_3d_path=False):
+        """Mapping network on [N, style_dim] (PixelNorm fused into the first EqualLinear launch).
+        reference_3d_path: evaluate what the reference's CUDA path computes when each z is fed as a [1,1,512] tensor
+        (`map_latents=True`, models/stylegan2.py:506-509): PixelNorm over the singleton axis (every element normalised
+        by itself) and bias[0] broadcast by the fused bias-act op (SURVEY.md §8(b) "Op API", §8(f) row 3)."""
         x = inputs.reshape(-1, inputs.shape[-1]).float()
         first = True
         for layer in self.style:
             if isinstance(layer, PixelNorm):
                 continue
-            x = layer(x, pixel_norm=first)
+            x = layer(x, pixel_norm=(2 if reference_3d_path else 1) if first else 0, bias0=reference_3d_path)
             first = False
         return x.view(*inputs.shape[:-1], -1)
 
@@ -470,8 +473,10 @@ class Generator(nn.Module):
                 transform_dict_list=[], map_latents=False, return_u8=False):
         if map_latents:
             # Reference: th.cat([self.style(s[None, None, :]) for s in styles]).repeat(1, n_latent, 1)
-            # (models/stylegan2.py:506-509).  We map through the 2-D path (SURVEY.md §8(c) caveat 3).
-            latent = self.get_latent(styles)[:, None, :]
+            # (models/stylegan2.py:506-509).  Default = bit-for-bit what the reference's CUDA path returns for that 3-D
+            # input (see get_latent); MAUA_MAP_LATENTS=2d selects the ordinary 2-D mapping network instead.
+            quirk = os.environ.get("MAUA_MAP_LATENTS", "reference") != "2d"
+            latent = self.get_latent(styles, reference_3d_path=quirk)[:, None, :]
             return latent.repeat(1, self.n_latent, 1)
 
         if not input_is_latent:

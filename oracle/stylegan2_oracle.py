@@ -131,6 +131,21 @@ def mapping(z, sd, n_mlp=8, lr_mlp=0.01):
     return x
 
 
+def mapping_3d_cuda(z, sd, n_mlp=8, lr_mlp=0.01):
+    """What `Generator(zs, map_latents=True)` returns per z on the reference's CUDA path (`models/stylegan2.py:506-509`
+    feeds `s[None, None, :]`, a [1,1,512] tensor): PixelNorm reduces over dim 1 — a singleton — so every element is
+    normalised by itself (`:20`), and the CUDA fused_bias_act indexes `b[(i / step_b) % size_b]` with
+    `step_b = prod(x.shape[2:]) = 512` (`op/fused_bias_act_kernel.cu:29,67-69`), i.e. bias[0] for every feature.
+    (The CPU fallback broadcasts differently and returns another shape, SURVEY.md §8(c) caveat 3; this restates the CUDA
+    kernel and is checked on the GPU box against the compiled reference op, tests/test_gpu_plugins.py.)"""
+    x = z * torch.rsqrt(z ** 2 + 1e-8)
+    for i in range(n_mlp):
+        w, b = sd[f"style.{i + 1}.weight"], sd[f"style.{i + 1}.bias"]
+        scale = (1 / math.sqrt(w.shape[1])) * lr_mlp
+        x = F.leaky_relu(F.linear(x, w * scale) + b[0] * lr_mlp, 0.2) * 2 ** 0.5
+    return x
+
+
 def modulated_conv2d(x, style_w, sd, prefix, demodulate=True, upsample=False):
     """`models/stylegan2.py:217-254`: per-sample modulated (+demodulated) weights, grouped conv;
     up path = stride-2 transposed conv to (2H+1)x(2W+1) followed by the 4x4 blur with pad (1,1)."""

@@ -82,8 +82,8 @@ def test_generator_api_surface():
     g, sd = make_generator(32, 2, 3, "tc")
     z = torch.randn(4, 512, device="cuda")
     with torch.no_grad():
-        lat = g(z, map_latents=True)
-        assert lat.shape == (4, g.n_latent, 512)
+        assert g(z, map_latents=True).shape == (4, g.n_latent, 512)   # values: tests/test_gpu_plugins.py
+        lat = g.get_latent(z)[:, None, :].repeat(1, g.n_latent, 1)
         g.truncation_latent = g.mean_latent(256)
         img, lat_out = g([z], return_latents=True, truncation=0.7, randomize_noise=False)
         assert img.shape == (4, 3, 32, 32) and lat_out.shape == (4, g.n_latent, 512)
