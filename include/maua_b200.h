@@ -26,6 +26,7 @@
  *   maua_noise_bias_act_f32   <- NoiseInjection.forward + FusedLeakyReLU.forward models/stylegan2.py:262-266, op/fused_act.py:82-97
  *   maua_torgb_f32            <- ToRGB.forward (1x1 modconv + bias + Upsample(skip))      models/stylegan2.py:356-365
  *   maua_rgb_to_u8_nhwc       <- render.split_batches clamp/scale/permute/astype(uint8)   render.py:40-43
+ *   maua_fit_frames_u8        <- 2048-wide frames cropped + PIL-resized to 1920x1080             render.py:98-105
  *   maua_bend_warp_f32        <- Translate / Zoom / Rotate network bends                  audioreactive/bend.py:51-102
  *   maua_perlin_noise         <- perlin_noise                                             audioreactive/latent.py:188-246
  */
@@ -243,6 +244,15 @@ int maua_chroma_weight_latents_f32(const float* chroma, const float* selection, 
 /* examples/default.py:20-21: x[t][e] = envelope[t]*target[e] + (1 - envelope[t])*x[t][e] */
 int maua_envelope_blend_f32(float* x, const float* envelope, const float* target, int n_frames, long long inner,
                             void* stream);
+
+/* render.py:98-105 on the device: crop [crop_y0:+crop_h, crop_x0:+crop_w] of uint8 NHWC frames [B,in_h,in_w,3] and
+ * resample to [B,out_h,out_w,3] exactly like PIL.Image.resize(..., BILINEAR) (Pillow ImagingResample: horizontal then
+ * vertical pass, 22-bit fixed-point coefficients, 8-bit rounding after each pass).  bounds_*: [out][2] (first source
+ * index inside the crop, tap count), coef_*: [out][ksize] int32 — DEVICE arrays built by the host from Pillow's
+ * precompute_coeffs rule (maua_stylegan2_b200/render.py:pillow_bilinear_coeffs). */
+int maua_fit_frames_u8(const uint8_t* in, uint8_t* out, int batch, int in_h, int in_w, int crop_y0, int crop_x0,
+                       int crop_h, int crop_w, int out_h, int out_w, const int* bounds_x, const int* coef_x, int ksize_x,
+                       const int* bounds_y, const int* coef_y, int ksize_y, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Network bending + looping noise

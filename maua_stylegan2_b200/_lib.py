@@ -63,6 +63,7 @@ SIGNATURES = {
     "maua_sosfilt_f32": [_p, _p, _ll, _p, _i, _p],
     "maua_chroma_weight_latents_f32": [_p, _p, _p, _i, _i, _ll, _p],
     "maua_envelope_blend_f32": [_p, _p, _p, _i, _ll, _p],
+    "maua_fit_frames_u8": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p],
     "maua_bend_warp_f32": [_p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "maua_perlin_noise": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
 }

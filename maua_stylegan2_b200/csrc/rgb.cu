@@ -204,7 +204,66 @@ __global__ void __launch_bounds__(256) rgb_to_u8_kernel(const float* __restrict_
   }
 }
 
+// Crop + two-pass fixed-point bilinear resample of uint8 NHWC frames, bit-for-bit what the reference's frame loop does
+// on the host per frame with PIL (render.py:98-105: img[:, 112:-112] -> Image.resize((1920, 1080), BILINEAR)):
+// Pillow's ImagingResample = horizontal pass then vertical pass, 22-bit integer coefficients, each pass rounded to
+// 8 bits ((1 << 21) + sum) >> 22, clipped).  One thread = one output pixel: it re-derives the <= ksize_y horizontally
+// resampled values it needs (upscaling: 3x3 source bytes per channel), so no intermediate image touches HBM.
+__global__ void __launch_bounds__(256) fit_frames_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                         int in_h, int in_w, int cy0, int cx0, int oh, int ow,
+                                                         const int* __restrict__ bx, const int* __restrict__ kx, int ksx,
+                                                         const int* __restrict__ by, const int* __restrict__ ky, int ksy,
+                                                         long long total) {
+  constexpr int PB = 22;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int xx = (int)(i % ow);
+    const long long r = i / ow;
+    const int yy = (int)(r % oh);
+    const long long b = r / oh;
+    const int x0 = __ldg(bx + 2 * xx) + cx0, nx = __ldg(bx + 2 * xx + 1);
+    const int y0 = __ldg(by + 2 * yy) + cy0, ny = __ldg(by + 2 * yy + 1);
+    const uint8_t* src = in + b * (long long)in_h * in_w * 3;
+    int acc[3] = {1 << (PB - 1), 1 << (PB - 1), 1 << (PB - 1)};
+    for (int j = 0; j < ny; ++j) {
+      const uint8_t* row = src + ((long long)(y0 + j) * in_w + x0) * 3;
+      int h[3] = {1 << (PB - 1), 1 << (PB - 1), 1 << (PB - 1)};
+      for (int t = 0; t < nx; ++t) {
+        const int k = __ldg(kx + xx * ksx + t);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) h[c] += (int)__ldg(row + t * 3 + c) * k;
+      }
+      const int kv = __ldg(ky + yy * ksy + j);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] += min(max(h[c] >> PB, 0), 255) * kv;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[i * 3 + c] = (uint8_t)min(max(acc[c] >> PB, 0), 255);
+  }
+}
+
 }  // namespace maua
+
+extern "C" int maua_fit_frames_u8(const uint8_t* in, uint8_t* out, int batch, int in_h, int in_w, int crop_y0,
+                                  int crop_x0, int crop_h, int crop_w, int out_h, int out_w, const int* bounds_x,
+                                  const int* coef_x, int ksize_x, const int* bounds_y, const int* coef_y, int ksize_y,
+                                  void* stream) {
+  using namespace maua;
+  MAUA_CHECK_ARG(in && out && in != out && bounds_x && coef_x && bounds_y && coef_y, "fit_frames: null or aliased pointers");
+  MAUA_CHECK_ARG(batch >= 0 && in_h >= 1 && in_w >= 1 && out_h >= 1 && out_w >= 1 && ksize_x >= 1 && ksize_y >= 1,
+                 "fit_frames: bad shape");
+  MAUA_CHECK_ARG(crop_y0 >= 0 && crop_x0 >= 0 && crop_h >= 1 && crop_w >= 1 && crop_y0 + crop_h <= in_h &&
+                     crop_x0 + crop_w <= in_w,
+                 "fit_frames: crop window outside the frame");
+  const long long total = (long long)batch * out_h * out_w;
+  if (total == 0) return MAUA_OK;
+  long long blocks = ceil_div(total, 256LL);
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  fit_frames_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(in, out, in_h, in_w, crop_y0, crop_x0, out_h, out_w,
+                                                                    bounds_x, coef_x, ksize_x, bounds_y, coef_y,
+                                                                    ksize_y, total);
+  MAUA_CHECK_LAUNCH("fit_frames");
+  return MAUA_OK;
+}
 
 extern "C" int maua_torgb_f32(const float* x, const float* wrgb, const float* s, const float* bias,
                               const float* skip, const float* k4, float* y, int batch, int cin, int h, int w,

@@ -34,7 +34,7 @@ class FramePipeline:
     """Batches -> generator -> uint8 NHWC frames in pinned host memory, double-buffered over two CUDA streams."""
 
     def __init__(self, generator, latents, noise, batch_size, truncation=1.0, bends=None, rewrites=None,
-                 randomize_noise=False, device=None, rank=0, world=1, use_graph=True):
+                 randomize_noise=False, device=None, rank=0, world=1, use_graph=True, fit_size=None):
         self.g = generator
         self.device = device or next(generator.parameters()).device
         self.batch = batch_size
@@ -48,6 +48,7 @@ class FramePipeline:
                 bend["modulation"] = _pin(bend["modulation"])
         self.rewrites = rewrites or {}
         self.randomize_noise = randomize_noise
+        self.fit_size = fit_size  # 1920 / 1080: 2048-wide (-tall) frames are cropped + resized on the device
         self.n_frames = len(self.latents)
         self.starts = list(range(0, self.n_frames, batch_size))
         self.copy_stream = torch.cuda.Stream(self.device)
@@ -241,6 +242,8 @@ class FramePipeline:
                 item = nxt if nxt is not None else self._stage(n)
                 nxt = self._stage(batch_start(i + 1)) if (i + 1 < steps and not graph_ok) else None
                 frames = self._render(item, n)
+            if self.fit_size in (1920, 1080):
+                frames = fit_frames(frames, self.fit_size)
             if frames.shape[0] < self.batch:  # short tail: pad by repeating the last frame (equal-size collective)
                 frames = torch.cat([frames, frames[-1:].expand(self.batch - frames.shape[0], -1, -1, -1)], 0)
             valid = min(self.n_frames - i * world * self.batch, world * self.batch)
@@ -309,18 +312,57 @@ class FFmpegSink:
         self.t.join()
 
 
-def _fit_output(frames, out_size):
-    """render.py:98-105: 2048-wide/tall generators are cropped and resized to 1920x1080 / 1080x1920."""
-    import PIL.Image
+def pillow_bilinear_coeffs(in_size, out_size):
+    """Pillow's `precompute_coeffs` + `normalize_coeffs_8bpc` (src/libImaging/Resample.c) for the BILINEAR filter
+    (support 1.0, triangle): per output index the first source index, the tap count and 22-bit fixed-point taps.
+    Host-side table construction only (a few KB); checked against PIL itself in tests/test_fit_frames.py."""
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.float64)
+    inv = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        n = min(int(center + support + 0.5), in_size) - xmin
+        v = np.abs((np.arange(n) + xmin - center + 0.5) * inv)
+        w = np.where(v < 1.0, 1.0 - v, 0.0)
+        total = w.sum()
+        kk[xx, :n] = w / total if total != 0.0 else w
+        bounds[xx] = (xmin, n)
+    fixed = np.where(kk < 0, np.trunc(-0.5 + kk * (1 << 22)), np.trunc(0.5 + kk * (1 << 22))).astype(np.int32)
+    return bounds, fixed
 
-    out = []
-    for img in frames:
-        if img.shape[1] == 2048:
-            img = np.array(PIL.Image.fromarray(img[:, 112:-112, :]).resize((1920, 1080), PIL.Image.BILINEAR))
-        elif img.shape[0] == 2048:
-            img = np.array(PIL.Image.fromarray(img[112:-112, :, :]).resize((1080, 1920), PIL.Image.BILINEAR))
-        out.append(img)
-    return np.stack(out)
+
+_FIT_TABLES = {}
+
+
+def fit_frames(frames, out_size):
+    """render.py:98-105 on the device: uint8 [n,H,W,3] frames of a 2048-wide (-tall) generator -> crop 112 px off both
+    ends of the long axis -> PIL-exact bilinear resize to 1920x1080 (1080x1920).  Other shapes pass through."""
+    from . import _lib as L
+
+    n, h, w, _ = frames.shape
+    if w == 2048:
+        crop, out_hw = (0, 112, h, w - 224), (1080, 1920)
+    elif h == 2048:
+        crop, out_hw = (112, 0, h - 224, w), (1920, 1080)
+    else:
+        return frames
+    key = (crop, out_hw, frames.device)
+    if key not in _FIT_TABLES:
+        bx, kx = pillow_bilinear_coeffs(crop[3], out_hw[1])
+        by, ky = pillow_bilinear_coeffs(crop[2], out_hw[0])
+        _FIT_TABLES[key] = tuple(torch.from_numpy(np.ascontiguousarray(t)).to(frames.device) for t in (bx, kx, by, ky))
+    bx, kx, by, ky = _FIT_TABLES[key]
+    frames = frames.contiguous()
+    out = torch.empty((n, out_hw[0], out_hw[1], 3), dtype=torch.uint8, device=frames.device)
+    L.call("maua_fit_frames_u8", frames.data_ptr(), out.data_ptr(), n, h, w, crop[0], crop[1], crop[2], crop[3],
+           out_hw[0], out_hw[1], bx.data_ptr(), kx.data_ptr(), kx.shape[1], by.data_ptr(), ky.data_ptr(), ky.shape[1],
+           L.stream_ptr(frames.device))
+    return out
 
 
 def render(generator, latents, noise, offset, duration, batch_size, out_size, output_file, audio_file=None,
@@ -334,12 +376,11 @@ def render(generator, latents, noise, offset, duration, batch_size, out_size, ou
         sink = FFmpegSink(output_file, w, h, len(latents) / duration, audio_file, offset, duration, ffmpeg_preset)
     if hasattr(generator, "module"):  # th.nn.DataParallel wrapper of the reference CLI (generate_audiovisual.py:54-55)
         generator = generator.module
-    pipe = FramePipeline(generator, latents, list(noise), batch_size, truncation, bends, rewrites, randomize_noise)
+    pipe = FramePipeline(generator, latents, list(noise), batch_size, truncation, bends, rewrites, randomize_noise,
+                         fit_size=out_size)
     pipe.warmup()
 
     def consume(frames):
-        if frames.shape[1] == 2048 or frames.shape[2] == 2048:
-            frames = _fit_output(frames, out_size)
         assert frames.shape[2] == w and frames.shape[1] == h, (
             f"generator's output image size does not match specified output size: \n"
             f"got: {frames.shape[2]}x{frames.shape[1]}\t\tshould be {w}x{h}")
