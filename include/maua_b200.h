@@ -219,6 +219,17 @@ int maua_audio_filterbank_f32(const float* spec, const float* fb, float* out, in
 int maua_audio_onset_env_f32(float* mel, float* env, float* scalar_ws, int n_frames, int n_mels, int pad, float amin,
                              float top_db, void* stream);
 /* librosa.feature.rms(S=|spec|) */
+/* madmom-flavoured onsets (reference default `type="mm"`, signal.py:52-67).
+ * stft_mm: FramedSignal(frame_size n_fft, hop, centred, zero padded) * np.hanning, circular shift n_fft/2, R2C ->
+ *          spec [n_frames][n_fft/2+1] (madmom drops the Nyquist bin: pass n_bins = n_fft/2 below).
+ * onsets_mm: fb [n_bands][n_bins] (LogarithmicFilterbank, transposed), band_lo/hi [n_bands] = bin range of each band
+ *          widened by one neighbour (ComplexFlux mask); onset[t] = spectral_diff + spectral_flux + superflux +
+ *          complex_flux + modified_kullback_leibler.  filt_ws: n_frames*n_bands floats, lgd_ws: n_frames*n_bins. */
+int maua_audio_stft_mm_f32(const float* y, long long n, float* spec, float* frames_ws, int n_fft, int hop, int n_frames,
+                           void* stream);
+int maua_audio_onsets_mm_f32(const float* spec, const float* fb, const int* band_lo, const int* band_hi, float* onset,
+                             float* filt_ws, float* lgd_ws, int n_frames, int spec_stride, int n_bins, int n_bands,
+                             int diff_frames, void* stream);
 int maua_audio_rms_f32(const float* spec, float* rms, int n_frames, int n_bins, int n_fft, void* stream);
 /* CENS post-processing of a chromagram [n_frames][n_chroma]: L1, quantise, hann(win_len) smoothing, L2. ws: same size */
 int maua_audio_cens_f32(const float* raw, float* cens, float* ws, int n_frames, int n_chroma, int win_len, void* stream);

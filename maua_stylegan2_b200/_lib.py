@@ -53,6 +53,8 @@ SIGNATURES = {
     "maua_audio_hpss_f32": [_p, _p, _p, _i, _i, _f, _f, _i, _p],
     "maua_audio_filterbank_f32": [_p, _p, _p, _i, _i, _i, _p],
     "maua_audio_onset_env_f32": [_p, _p, _p, _i, _i, _i, _f, _f, _p],
+    "maua_audio_stft_mm_f32": [_p, _ll, _p, _p, _i, _i, _i, _p],
+    "maua_audio_onsets_mm_f32": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "maua_audio_rms_f32": [_p, _p, _i, _i, _i, _p],
     "maua_audio_cens_f32": [_p, _p, _p, _i, _i, _i, _p],
     "maua_audio_nn_filter_f32": [_p, _p, _p, _i, _i, _i, _i, _p],

@@ -1,4 +1,5 @@
-"""Host-side construction of the mel and chroma filterbanks (setup only, a few KB; the projection runs on device).
+"""Host-side construction of the mel, chroma and logarithmic filterbanks (setup only, a few KB; the projection runs on
+device).
 Slaney-style mel bank and the STFT chroma bank as published for librosa.filters.mel / librosa.filters.chroma
 (the reference calls them through `rosa.onset.onset_strength`, signal.py:51, and `rosa.feature.chroma_*`, :115-119)."""
 import numpy as np
@@ -45,3 +46,42 @@ def chroma(sr, n_fft=2048, n_chroma=12, ctroct=5.0, octwidth=2.0):
     w *= np.tile(np.exp(-0.5 * (((frqbins / n_chroma - ctroct) / octwidth) ** 2)), (n_chroma, 1))
     w = np.roll(w, -3 * (n_chroma // 12), axis=0)
     return np.ascontiguousarray(w[:, :1 + n_fft // 2], dtype=np.float32)
+
+
+def log_filterbank(sr, n_bins=1024, bands_per_octave=24, fmin=30.0, fmax=17000.0, fref=440.0):
+    """madmom.audio.filters.LogarithmicFilterbank(bin_frequencies, num_bands=24, fmin, fmax, fref=440, norm_filters=True,
+    unique_filters=True) as published (the reference builds it through FilteredSpectrogram, signal.py:57):
+    semitone-fraction centre frequencies around A4 -> nearest FFT bins (duplicates dropped) -> overlapping triangular
+    filters over consecutive bin triples, each normalised to unit area.  Returns (fb [n_filters, n_bins] float32,
+    lo [n_filters], hi [n_filters]) with [lo, hi) = the filter's non-zero bins widened by one neighbour (the range
+    ComplexFlux takes its local-group-delay minimum over)."""
+    bin_freqs = np.fft.fftfreq(n_bins * 2, 1.0 / sr)[:n_bins]
+    left = np.floor(np.log2(float(fmin) / fref) * bands_per_octave)
+    right = np.ceil(np.log2(float(fmax) / fref) * bands_per_octave)
+    freqs = fref * 2.0 ** (np.arange(left, right) / float(bands_per_octave))
+    freqs = freqs[np.searchsorted(freqs, fmin):]
+    freqs = freqs[:np.searchsorted(freqs, fmax, "right")]
+    idx = np.clip(bin_freqs.searchsorted(freqs), 1, len(bin_freqs) - 1)
+    lo_f, hi_f = bin_freqs[idx - 1], bin_freqs[idx]
+    idx = np.unique(idx - (freqs - lo_f < hi_f - freqs))
+    if len(idx) < 3:
+        raise ValueError("log_filterbank: fewer than 3 distinct bins between fmin and fmax")
+    rows = []
+    for start, center, stop in zip(idx[:-2], idx[1:-1], idx[2:]):
+        if stop - start < 2:
+            center, stop = start, start + 1
+        tri = np.zeros(stop - start)
+        tri[:center - start] = np.linspace(0, 1, center - start, endpoint=False)
+        tri[center - start:] = np.linspace(1, 0, stop - center, endpoint=False)
+        tri /= tri.sum()
+        row = np.zeros(n_bins)
+        a, b = max(start, 0), min(stop, n_bins)
+        row[a:b] = tri[a - start:b - start]
+        rows.append(row)
+    fb = np.ascontiguousarray(np.stack(rows), dtype=np.float32)
+    lo = np.zeros(len(rows), np.int32)
+    hi = np.zeros(len(rows), np.int32)
+    for i, row in enumerate(fb):
+        nz = np.nonzero(row)[0]
+        lo[i], hi[i] = max(nz[0] - 1, 0), min(nz[-1] + 2, n_bins)
+    return fb, lo, hi

@@ -7,15 +7,14 @@ gaussian filter -> percentile clip.  Results are CUDA tensors (the reference ret
 `OUTPUT_DEVICE = "cpu"` for legacy hook files that mix them with CPU latents).
 
 Differences from the reference, all forced by its un-vendored dependencies (parity unpinned):
-  * `onsets(type="mm")` (madmom, the reference default) is not available; it falls back to the librosa-flavoured
-    algorithm (`type="rosa"`, signal.py:50-51) with a one-time warning.
+  * `onsets(type="mm")` (madmom, the reference default) and `type="rosa"` (librosa) are both restated from the
+    libraries' published algorithms.
   * `chroma`: the CQT front-end of chroma_cens is replaced by the STFT chroma filterbank (north_star: cuFFT-fronted);
     CENS post-processing and the cosine k-NN median filter follow the published librosa algorithms.
   * `laplacian_segmentation` is out of scope.
 """
 import math
 import os
-import warnings
 from pathlib import Path
 
 import numpy as np
@@ -134,17 +133,45 @@ def _resample_clipped(x, n_frames):
 # reference API
 # ---------------------------------------------------------------------------------------------------------------
 
-_warned_mm = False
+MM_FRAME, MM_HOP = 2048, 441
+
+
+def onset_strength_mm(y, sr, fmin, fmax):
+    """The madmom half of signal.py:52-67: FramedSignal(2048, hop 441) -> STFT(circular_shift) -> |.| ->
+    24-bands-per-octave LogarithmicFilterbank(fmin, fmax) -> spectral_diff + spectral_flux + superflux + complex_flux +
+    modified_kullback_leibler, one value per hop (csrc/audio.cu, madmom restated — parity unpinned)."""
+    y = _to_dev(y)
+    n = y.numel()
+    T = int(math.ceil(n / float(MM_HOP)))
+    n_bins = MM_FRAME // 2
+    spec = th.empty((T, n_bins + 1, 2), device=y.device, dtype=th.float32)
+    ws = th.empty(T * MM_FRAME, device=y.device, dtype=th.float32)
+    L.call("maua_audio_stft_mm_f32", y.data_ptr(), n, spec.data_ptr(), ws.data_ptr(), MM_FRAME, MM_HOP, T,
+           L.stream_ptr(y.device))
+    fb, lo, hi = filters.log_filterbank(sr, n_bins, 24, fmin, fmax)
+    fb_d, lo_d, hi_d = (th.from_numpy(a).to(y.device) for a in (fb, lo, hi))
+    # madmom's SpectrogramDifference: frames to look back = the hop count that spans half of the window's half-width
+    win = np.hanning(MM_FRAME)
+    diff_frames = int(max(1, round((MM_FRAME / 2 - np.argmax(win > 0.5 * win.max())) / MM_HOP)))
+    onset = th.empty(T, device=y.device, dtype=th.float32)
+    filt = th.empty((T, fb.shape[0]), device=y.device, dtype=th.float32)
+    lgd = th.empty((T, n_bins), device=y.device, dtype=th.float32)
+    L.call("maua_audio_onsets_mm_f32", spec.data_ptr(), fb_d.data_ptr(), lo_d.data_ptr(), hi_d.data_ptr(),
+           onset.data_ptr(), filt.data_ptr(), lgd.data_ptr(), T, n_bins + 1, n_bins, fb.shape[0], diff_frames,
+           L.stream_ptr(y.device))
+    return onset
 
 
 def onsets(audio, sr, n_frames, margin=8, fmin=20, fmax=8000, smooth=1, clip=100, power=1, type="mm"):
-    """signal.py:31-73"""
-    global _warned_mm
-    if type == "mm" and not _warned_mm:
-        warnings.warn("madmom onset flavour is not available on the device path; using the librosa flavour (type='rosa')")
-        _warned_mm = True
+    """signal.py:31-73: percussive separation -> onset strength (librosa flavour "rosa" or madmom flavour "mm", the
+    reference default) -> Fourier resample to n_frames -> causal-0 gaussian -> percentile clip -> power."""
     y_perc = percussive(audio, margin=margin)
-    onset = onset_strength(y_perc, sr, fmin, fmax)
+    if type == "rosa":
+        onset = onset_strength(y_perc, sr, fmin, fmax)
+    elif type == "mm":
+        onset = onset_strength_mm(y_perc, sr, fmin, fmax)
+    else:
+        raise ValueError(f"onsets: unknown type {type!r} (expected 'rosa' or 'mm')")
     onset = _resample_clipped(onset, n_frames)
     onset = gaussian_filter(onset, smooth, causal=0)
     onset = percentile_clip(onset, clip)

@@ -540,6 +540,111 @@ __global__ void envelope_blend_kernel(float* __restrict__ x, const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// madmom-flavoured onsets (the reference's DEFAULT `type="mm"`, audioreactive/signal.py:52-67; madmom is un-vendored:
+// restated from its published algorithm — FramedSignal / ShortTimeFourierTransform(circular_shift) /
+// LogarithmicFilterbank / features.onsets.{spectral_diff, spectral_flux, superflux, complex_flux,
+// modified_kullback_leibler}; parity unpinned)
+// ---------------------------------------------------------------------------------------------------------------
+// FramedSignal(frame_size, hop, origin 0): frame t = samples [t*hop - n_fft/2, +n_fft), zeros outside; symmetric
+// np.hanning window; circular shift by n_fft/2 so that phases are referenced to the frame centre.
+__global__ void frame_mm_kernel(const float* __restrict__ y, long long n, float* __restrict__ frames, int n_fft, int hop,
+                                long long total) {
+  const int half = n_fft / 2;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int k = (int)(i % n_fft);             // position in the SHIFTED frame
+    const long long t = i / n_fft;
+    const int ks = k < half ? k + half : k - half;  // position in the windowed frame
+    const long long p = t * hop + ks - half;
+    const float w = 0.5f - 0.5f * cospif(2.f * ks / (n_fft - 1));
+    frames[i] = (p >= 0 && p < n) ? y[p] * w : 0.f;
+  }
+}
+
+// per frame: filtered magnitude spectrogram row and |local group delay| / pi row
+__global__ void __launch_bounds__(256) mm_filt_lgd_kernel(const float2* __restrict__ S, const float* __restrict__ fb,
+                                                          float* __restrict__ filt, float* __restrict__ lgd, int Fs,
+                                                          int F, int NB) {
+  extern __shared__ float sm[];  // mag[F], phase[F]
+  float* mag = sm;
+  float* ph = sm + F;
+  const int t = blockIdx.x;
+  for (int f = threadIdx.x; f < F; f += 256) {
+    const float2 v = S[(long long)t * Fs + f];
+    mag[f] = sqrtf(v.x * v.x + v.y * v.y);
+    ph[f] = atan2f(v.y, v.x);
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < F; f += 256) {
+    float g = 0.f;
+    if (f + 1 < F) {
+      // np.unwrap along frequency, then lgd[f] = up[f] - up[f+1]: minus the wrapped phase step
+      const float dd = ph[f + 1] - ph[f];
+      float dm = dd + kPi;
+      dm = dm - 2.f * kPi * floorf(dm / (2.f * kPi)) - kPi;
+      if (dm == -kPi && dd > 0.f) dm = kPi;
+      g = fabsf(fabsf(dd) < kPi ? dd : dm) / kPi;
+    }
+    lgd[(long long)t * F + f] = g;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = warp; b < NB; b += 8) {
+    float acc = 0.f;
+    for (int f = lane; f < F; f += 32) acc = fmaf(mag[f], __ldg(fb + (long long)b * F + f), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) filt[(long long)t * NB + b] = acc;
+  }
+}
+
+// per frame: sum of the five onset detection functions
+__global__ void __launch_bounds__(128) mm_onset_kernel(const float* __restrict__ filt, const float* __restrict__ lgd,
+                                                       const int* __restrict__ band_lo, const int* __restrict__ band_hi,
+                                                       float* __restrict__ onset, int T, int F, int NB, int diff_frames,
+                                                       float eps) {
+  const int t = blockIdx.x;
+  float sd = 0.f, sf = 0.f, su = 0.f, cf = 0.f, kl = 0.f;
+  const int tp = t - diff_frames;
+  for (int b = threadIdx.x; b < NB; b += 128) {
+    const float cur = filt[(long long)t * NB + b];
+    if (tp >= 0) {
+      const float* prev = filt + (long long)tp * NB;
+      const float d = fmaxf(cur - prev[b], 0.f);
+      sd = fmaf(d, d, sd);
+      sf += d;
+      // SuperFlux: previous frame max-filtered over 3 bands (scipy maximum_filter, 'reflect' edges)
+      const float pm = fmaxf(prev[b], fmaxf(prev[b > 0 ? b - 1 : 0], prev[b + 1 < NB ? b + 1 : NB - 1]));
+      const float dm = fmaxf(cur - pm, 0.f);
+      su += dm;
+      // ComplexFlux mask: min over the band's bins (+1 neighbour each side) of the 3-frame temporal max of |lgd|
+      float mask = 3.0e38f;
+      const int tm = t > 0 ? t - 1 : 0, tn = t + 1 < T ? t + 1 : T - 1;
+      for (int f = band_lo[b]; f < band_hi[b]; ++f) {
+        const float g = fmaxf(lgd[(long long)t * F + f], fmaxf(lgd[(long long)tm * F + f], lgd[(long long)tn * F + f]));
+        mask = fminf(mask, g);
+      }
+      cf = fmaf(dm, mask, cf);
+    }
+    if (t >= 1) kl += log1pf(cur / (filt[(long long)(t - 1) * NB + b] + eps));
+  }
+  __shared__ float red[5][4];
+  float v[5] = {sd, sf, su, cf, kl};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    if (lane == 0) red[i][warp] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) tot[i] = red[i][0] + red[i][1] + red[i][2] + red[i][3];
+    onset[t] = tot[0] + tot[1] + tot[2] + tot[3] + tot[4] / (float)NB;
+  }
+}
+
 static inline unsigned nblocks(long long work, int per = 256, long long cap = 148LL * 16) {
   long long b = (work + per - 1) / per;
   if (b > cap) b = cap;
@@ -635,6 +740,40 @@ extern "C" int maua_audio_onset_env_f32(float* mel, float* env, float* scalar_ws
   MAUA_CHECK_LAUNCH("onset_env(db)");
   onset_env_kernel<<<ceil_div(n_frames, 8), dim3(32, 8), 0, st>>>(mel, scalar_ws, top_db, env, n_frames, n_mels, pad);
   MAUA_CHECK_LAUNCH("onset_env(diff)");
+  return MAUA_OK;
+}
+
+extern "C" int maua_audio_stft_mm_f32(const float* y, long long n, float* spec, float* frames_ws, int n_fft, int hop,
+                                      int n_frames, void* stream) {
+  MAUA_CHECK_ARG(y && spec && frames_ws && n >= 1 && n_fft >= 4 && n_fft % 2 == 0 && hop >= 1 && n_frames >= 1,
+                 "stft_mm: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  const long long total = (long long)n_frames * n_fft;
+  frame_mm_kernel<<<nblocks(total), 256, 0, st>>>(y, n, frames_ws, n_fft, hop, total);
+  MAUA_CHECK_LAUNCH("stft_mm(frame)");
+  cufftHandle plan;
+  int rc = get_plan(0, n_fft, n_frames, 1, current_device(), &plan);
+  if (rc) return rc;
+  MAUA_CHECK_FFT(cufftSetStream(plan, st));
+  MAUA_CHECK_FFT(cufftExecR2C(plan, frames_ws, reinterpret_cast<cufftComplex*>(spec)));
+  count_launch();
+  return MAUA_OK;
+}
+
+extern "C" int maua_audio_onsets_mm_f32(const float* spec, const float* fb, const int* band_lo, const int* band_hi,
+                                        float* onset, float* filt_ws, float* lgd_ws, int n_frames, int spec_stride,
+                                        int n_bins, int n_bands, int diff_frames, void* stream) {
+  MAUA_CHECK_ARG(spec && fb && band_lo && band_hi && onset && filt_ws && lgd_ws, "onsets_mm: null pointers");
+  MAUA_CHECK_ARG(n_frames >= 1 && n_bins >= 2 && n_bins <= spec_stride && n_bins <= 8192 && n_bands >= 1 &&
+                     diff_frames >= 1,
+                 "onsets_mm: bad shape");
+  cudaStream_t st = as_stream(stream);
+  mm_filt_lgd_kernel<<<n_frames, 256, 2 * (size_t)n_bins * sizeof(float), st>>>(
+      reinterpret_cast<const float2*>(spec), fb, filt_ws, lgd_ws, spec_stride, n_bins, n_bands);
+  MAUA_CHECK_LAUNCH("onsets_mm(filter+lgd)");
+  mm_onset_kernel<<<n_frames, 128, 0, st>>>(filt_ws, lgd_ws, band_lo, band_hi, onset, n_frames, n_bins, n_bands,
+                                            diff_frames, 2.220446049250313e-16f);
+  MAUA_CHECK_LAUNCH("onsets_mm(sum)");
   return MAUA_OK;
 }
 

@@ -226,10 +226,92 @@ def percentile_clip(sig, p):
     return s / s.max()
 
 
-def onsets(audio, sr, n_frames, margin=8, fmin=20, fmax=8000, smooth=1, clip=100, power=1, smf=1.0):
-    """signal.py:31-73 with type='rosa'."""
+# ---- madmom (un-vendored, unpinned in requirements.txt; absent here): restated from its published source -------------
+def mm_log_filterbank(sr, n_bins=1024, bands_per_octave=24, fmin=30.0, fmax=17000.0, fref=440.0):
+    """madmom.audio.filters: log_frequencies -> frequencies2bins(unique) -> TriangularFilter.filters(norm, overlap)
+    -> Filterbank.from_filters.  Returns [n_bins, n_filters]."""
+    bin_freqs = np.fft.fftfreq(n_bins * 2, 1.0 / sr)[:n_bins]
+    left = np.floor(np.log2(float(fmin) / fref) * bands_per_octave)
+    right = np.ceil(np.log2(float(fmax) / fref) * bands_per_octave)
+    f = fref * 2.0 ** (np.arange(left, right) / float(bands_per_octave))
+    f = f[np.searchsorted(f, fmin):]
+    f = f[:np.searchsorted(f, fmax, "right")]
+    idx = np.clip(bin_freqs.searchsorted(f), 1, len(bin_freqs) - 1)
+    idx = idx - ((f - bin_freqs[idx - 1]) < (bin_freqs[idx] - f))
+    bins = np.unique(idx)
+    filters = []
+    i = 0
+    while i + 3 <= len(bins):
+        start, center, stop = bins[i:i + 3]
+        i += 1
+        if stop - start < 2:
+            center, stop = start, start + 1
+        data = np.zeros(stop - start)
+        data[:center - start] = np.linspace(0, 1, center - start, endpoint=False)
+        data[center - start:] = np.linspace(1, 0, stop - center, endpoint=False)
+        filters.append((start, data / data.sum()))
+    fb = np.zeros((n_bins, len(filters)), np.float32)
+    for b, (start, data) in enumerate(filters):
+        seg = fb[start:start + len(data), b]
+        np.maximum(data[:len(seg)], seg, out=seg)
+    return fb
+
+
+def mm_stft(y, frame_size=2048, hop=441):
+    """FramedSignal(origin 0, end 'normal') + ShortTimeFourierTransform(window=np.hanning, circular_shift=True):
+    complex spectrogram [T, frame_size/2] (no Nyquist bin)."""
+    y = np.asarray(y, np.float32)
+    T = int(np.ceil(len(y) / float(hop)))
+    win = np.hanning(frame_size).astype(np.float32)
+    out = np.zeros((T, frame_size // 2), np.complex64)
+    pad = np.concatenate([np.zeros(frame_size // 2, np.float32), y, np.zeros(frame_size + hop, np.float32)])
+    for t in range(T):
+        fr = pad[t * hop:t * hop + frame_size] * win           # starts at t*hop - frame_size/2 in the unpadded signal
+        fr = np.concatenate([fr[frame_size // 2:], fr[:frame_size // 2]])
+        out[t] = np.fft.fft(fr)[:frame_size // 2]
+    return out
+
+
+def onset_strength_mm(y, sr, fmin, fmax, frame_size=2048, hop=441):
+    """signal.py:53-66: sum of madmom.features.onsets.{spectral_diff, spectral_flux, superflux, complex_flux,
+    modified_kullback_leibler} on the 24-bands/octave filtered magnitude spectrogram."""
+    from scipy.ndimage import maximum_filter
+
+    S = mm_stft(y, frame_size, hop)
+    fb = mm_log_filterbank(sr, frame_size // 2, 24, fmin, fmax)
+    spec = np.abs(S).astype(np.float32) @ fb
+    win = np.hanning(frame_size)
+    df = int(max(1, round((len(win) / 2 - np.argmax(win > 0.5 * max(win))) / hop)))
+
+    def diff(max_bins=None):
+        ref = maximum_filter(spec, size=(1, max_bins)) if max_bins else spec
+        d = np.zeros_like(spec)
+        d[df:] = spec[df:] - ref[:-df]
+        return np.maximum(d, 0)
+
+    sd = np.sum(diff() ** 2, axis=1)
+    sf = np.sum(diff(), axis=1)
+    su = np.sum(diff(3), axis=1)
+    phase = np.angle(S)
+    up = np.unwrap(phase)
+    up[:, :-1] -= up[:, 1:]
+    up[:, -1] = 0
+    lgd = maximum_filter(np.abs(up) / np.pi, size=[3, 1])
+    mask = np.zeros_like(spec)
+    for b in range(spec.shape[1]):
+        nz = np.nonzero(fb[:, b])[0]
+        mask[:, b] = np.amin(lgd[:, max(nz[0] - 1, 0):min(nz[-1] + 2, lgd.shape[1])], axis=1)
+    cf = np.sum(diff(3) * mask, axis=1)
+    mkl = np.zeros_like(spec)
+    mkl[1:] = spec[1:] / (spec[:-1] + np.float32(np.spacing(1)))
+    kl = np.mean(np.log(1 + mkl), axis=1)
+    return (sd + sf + su + cf + kl).astype(np.float32)
+
+
+def onsets(audio, sr, n_frames, margin=8, fmin=20, fmax=8000, smooth=1, clip=100, power=1, smf=1.0, type="rosa"):
+    """signal.py:31-73."""
     y_perc = percussive(audio, margin=margin)
-    o = onset_strength(y_perc, sr, fmin, fmax)
+    o = onset_strength_mm(y_perc, sr, fmin, fmax) if type == "mm" else onset_strength(y_perc, sr, fmin, fmax)
     o = np.clip(resample(o, n_frames), o.min(), o.max()).astype(np.float32)
     o = gaussian_filter(o, smooth, causal=0, smf=smf)
     o = percentile_clip(o, clip)

@@ -153,3 +153,30 @@ def test_generate_end_to_end_small():
     allf = np.concatenate(frames)
     assert allf.shape == (30, 32, 32, 3) and allf.dtype == np.uint8
     assert len({f.tobytes() for f in allf}) > 20, "frames must react to the audio (not all identical)"
+
+
+def test_madmom_flavoured_onsets_vs_oracle():
+    """The reference default `onsets(type="mm")` (signal.py:52-67): device chain vs the numpy restatement of madmom."""
+    from maua_stylegan2_b200.audioreactive import filters
+    from maua_stylegan2_b200.audioreactive import signal as S
+
+    S.set_SMF(1)
+    y = _audio(3.0, seed=6)
+    for fmin, fmax in ((20, 8000), (20, 150), (500, 8000)):
+        fb, lo, hi = filters.log_filterbank(SR, 1024, 24, fmin, fmax)
+        assert np.array_equal(fb.T, A.mm_log_filterbank(SR, 1024, 24, fmin, fmax))
+        assert (lo < hi).all() and lo.min() >= 0 and hi.max() <= 1024
+    # the detection functions on the SAME percussive signal (isolates them from the HPSS/ISTFT front-end)
+    y_perc = S.percussive(y, 8).cpu().numpy()
+    env = S.onset_strength_mm(y_perc, SR, 20, 8000).cpu().numpy()
+    want = A.onset_strength_mm(y_perc, SR, 20, 8000)
+    assert env.shape == want.shape == (int(np.ceil(len(y) / 441)),)
+    assert np.abs(env - want).max() < 2e-3 * want.max(), np.abs(env - want).max() / want.max()
+    n_frames = 90
+    for kw in (dict(fmax=150, smooth=5, clip=97, power=2), dict(fmin=500, smooth=5, clip=99, power=2), dict()):
+        got = S.onsets(y, SR, n_frames, **kw).cpu().numpy()          # type="mm" is the default, as in the reference
+        ref = A.onsets(y, SR, n_frames, type="mm", **kw)
+        assert got.shape == (n_frames,) and got.min() >= 0 and got.max() <= 1 + 1e-6
+        assert np.abs(got - ref).max() < 2e-2, kw
+    with pytest.raises(ValueError):
+        S.onsets(y, SR, n_frames, type="nope")
