@@ -16,6 +16,7 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -46,6 +47,7 @@ struct Params {
   int n_phase;           // accumulator phases per item: 1 same-res; transposed: 4 / 2 / 1 (4 / n_groups)
   int n_groups;          // transposed only: phase groups walked as separate work items (1, 2 or 4)
   int n_items;           // work items = n_tiles * tiles_x * tiles_y * B, walked with stride gridDim.x
+  int dbg;               // MAUA_TC_DBG (timing experiments, results invalid): 1 = empty epilogue, 2 = no A loads after the first
 };
 
 // Tap lists.  same-res: tap (ky,kx) reads x[y+ky-1, x+kx-1] -> halo (ky, kx), one accumulator phase.
@@ -69,7 +71,9 @@ __constant__ TapList c_taps[8] = {
 
 __device__ __forceinline__ float lrelu_s(float v, float slope, float scale) { return (v > 0.f ? v : v * slope) * scale; }
 
-template <int KC, bool UP>
+// MODE: 0 = one product (hi*hi), 1 = three products as three N = BN MMAs, 2 = "concat": hi*[hi|lo] as one N = 2*BN MMA
+// plus lo*hi.  A template parameter (not p.nprod / p.cat) so that the issue loop is branch-free.
+template <int KC, bool UP, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -88,7 +92,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const uint32_t b_full = a_empty + 8 * p.SA, b_empty = b_full + 8 * p.SB;
   const uint32_t acc_full = b_empty + 8 * p.SB, acc_empty = acc_full + 8 * p.AS;
   const uint32_t tmem_slot = acc_empty + 8 * p.AS;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then KNOWS it is warp-uniform, so the role branches below are uniform
+  // branches and loop state / descriptors of the single-role loops live in uniform registers (no R2UR per MMA)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi);
@@ -143,10 +149,14 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       for (int kc = 0; kc < p.n_kchunks; ++kc) {
         const int c0 = kc * KC;
         mbar_wait(a_empty + 8 * ia, pa ^ 1);
+        if ((p.dbg & 2) && item != (int)blockIdx.x) {
+          mbar_arrive(a_full + 8 * ia);
+        } else {
         mbar_expect_tx(a_full + 8 * ia, halo_bytes * (p.nprod > 1 ? 2 : 1));
         const uint32_t dst = a_base + ia * a_stage;
         tma_load_4d(dst, &tm_a_hi, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
         if (p.nprod > 1) tma_load_4d(dst + p.a_plane, &tm_a_lo, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
+        }
         if (++ia == p.SA) { ia = 0; pa ^= 1; }
 #pragma unroll 1
         for (int t = 0; t < tl.n; ++t) {
@@ -174,7 +184,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const uint64_t a_stage16 = a_stage >> 4, a_plane16 = p.a_plane >> 4;
     const uint64_t b_stage16 = b_stage >> 4, b_half16 = b_half >> 4;
     const uint32_t rstep16 = (uint32_t)(TH * p.HW_) * ROW >> 4;  // next stacked tile: 16 halo rows further
-    const int mode = p.nprod == 1 ? 0 : (p.cat ? 2 : 1);
+    constexpr int mode = MODE;
     int ia = 0, ib = 0, as = 0;
     uint32_t pa = 0, pb = 0, pacc = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -185,49 +195,58 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       tc_fence_after();
       const uint32_t acc_stage = tmem_base + (uint32_t)as * acc_cols;
       uint32_t started = 0;  // bit ph: the accumulators of phase ph have received their first MMA
-      for (int kc = 0; kc < p.n_kchunks; ++kc) {
-        mbar_wait(a_full + 8 * ia, pa);
-        const uint64_t da_stage = da0 + (uint64_t)ia * a_stage16;
+      // R is a compile-time constant inside the tap loop (generic lambda + switch): the R x (2..6) MMAs of a tap are
+      // fully unrolled, so their descriptors sit in distinct uniform registers and the UTCHMMAs issue back to back —
+      // with a rolled r loop the warp stalled once per 4 MMAs until the tensor core had consumed the operand registers.
+      auto run_item = [&](auto rc) {
+        constexpr int RR = decltype(rc)::value;
+        for (int kc = 0; kc < p.n_kchunks; ++kc) {
+          mbar_wait(a_full + 8 * ia, pa);
+          const uint64_t da_stage = da0 + (uint64_t)ia * a_stage16;
 #pragma unroll 1
-        for (int t = 0; t < tl.n; ++t) {
-          const Tap tp = tl.t[t];
-          if (!p.resident_b || item == (int)blockIdx.x) {
-            mbar_wait(b_full + 8 * ib, pb);
-            tc_fence_after();
-          }
-          const uint64_t dbh = db0 + (uint64_t)ib * b_stage16, dbl = dbh + b_half16;
-          uint64_t dah = da_stage + (uint64_t)((uint32_t)(tp.hy * p.HW_ + tp.hx) * ROW >> 4);
-          uint32_t acc = acc_stage + (uint32_t)(tp.phase * p.R) * blk_cols;
-          const uint32_t first = (started >> tp.phase) & 1u;
-#pragma unroll 1
-          for (int r = 0; r < p.R; ++r) {
-            const uint64_t dal = dah + a_plane16;
-            if (!leader) {
-            } else if (mode == 2) {  // [hi*hi | hi*lo] in one N = 2*BN MMA (B stage = hi rows followed by lo rows), then lo*hi
-              umma_bf16(acc, dah, dbh, idesc2, first);
-              umma_bf16(acc, dah + 2, dbh + 2, idesc2, 1u);
-              umma_bf16(acc, dal, dbh, idesc, 1u);
-              umma_bf16(acc, dal + 2, dbh + 2, idesc, 1u);
-            } else {
-              umma_bf16(acc, dah, dbh, idesc, first);
-              umma_bf16(acc, dah + 2, dbh + 2, idesc, 1u);
-              if (mode == 1) {
-                umma_bf16(acc, dah, dbl, idesc, 1u);
-                umma_bf16(acc, dah + 2, dbl + 2, idesc, 1u);
-                umma_bf16(acc, dal, dbh, idesc, 1u);
-                umma_bf16(acc, dal + 2, dbh + 2, idesc, 1u);
+          for (int t = 0; t < tl.n; ++t) {
+            const Tap tp = tl.t[t];
+            if (!p.resident_b || item == (int)blockIdx.x) {
+              mbar_wait(b_full + 8 * ib, pb);
+              tc_fence_after();
+            }
+            const uint64_t dbh = db0 + (uint64_t)ib * b_stage16, dbl = dbh + b_half16;
+            const uint64_t dah0 = da_stage + (uint64_t)((uint32_t)(tp.hy * p.HW_ + tp.hx) * ROW >> 4);
+            const uint32_t acc0 = acc_stage + (uint32_t)(tp.phase * RR) * blk_cols;
+            const uint32_t first = (started >> tp.phase) & 1u;
+            if (leader) {
+#pragma unroll
+              for (int r = 0; r < RR; ++r) {
+                const uint64_t dah = dah0 + (uint64_t)r * rstep16, dal = dah + a_plane16;
+                const uint32_t acc = acc0 + (uint32_t)r * blk_cols;
+                if (mode == 2) {  // [hi*hi | hi*lo] in one N = 2*BN MMA (B stage = hi rows then lo rows), then lo*hi
+                  umma_bf16(acc, dah, dbh, idesc2, first);
+                  umma_bf16(acc, dah + 2, dbh + 2, idesc2, 1u);
+                  umma_bf16(acc, dal, dbh, idesc, 1u);
+                  umma_bf16(acc, dal + 2, dbh + 2, idesc, 1u);
+                } else {
+                  umma_bf16(acc, dah, dbh, idesc, first);
+                  umma_bf16(acc, dah + 2, dbh + 2, idesc, 1u);
+                  if (mode == 1) {
+                    umma_bf16(acc, dah, dbl, idesc, 1u);
+                    umma_bf16(acc, dah + 2, dbl + 2, idesc, 1u);
+                    umma_bf16(acc, dal, dbh, idesc, 1u);
+                    umma_bf16(acc, dal + 2, dbh + 2, idesc, 1u);
+                  }
+                }
               }
             }
-            dah += rstep16;
-            acc += blk_cols;
+            started |= 1u << tp.phase;
+            if (!p.resident_b && leader) umma_commit(b_empty + 8 * ib);
+            if (++ib == p.SB) { ib = 0; pb ^= 1; }
           }
-          started |= 1u << tp.phase;
-          if (!p.resident_b && leader) umma_commit(b_empty + 8 * ib);
-          if (++ib == p.SB) { ib = 0; pb ^= 1; }
+          if (leader) umma_commit(a_empty + 8 * ia);
+          if (++ia == p.SA) { ia = 0; pa ^= 1; }
         }
-        if (leader) umma_commit(a_empty + 8 * ia);
-        if (++ia == p.SA) { ia = 0; pa ^= 1; }
-      }
+      };
+      if (p.R == 4) run_item(std::integral_constant<int, 4>{});
+      else if (p.R == 2) run_item(std::integral_constant<int, 2>{});
+      else run_item(std::integral_constant<int, 1>{});
       if (leader) umma_commit(acc_full + 8 * as);
       if (++as == p.AS) { as = 0; pacc ^= 1; }
     }
@@ -242,7 +261,11 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const float nwv = (!UP && ep.activate && ep.noise) ? __ldg(ep.noise_weight) : 0.f;
     int as = 0;
     uint32_t pacc = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    // fused ToRGB hands whole tiles to a warp (fixed summation order); tile r of the CTA's it-th item goes to epilogue
+    // group (it*R + r) % EPI_GROUPS, so that R = 2 / R = 4 items load the three groups evenly over consecutive items
+    // (a fixed r % EPI_GROUPS left one group idle for R = 2 and gave one group half of the work for R = 4)
+    int job0 = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, job0 = (job0 + p.R) % EPI_GROUPS) {
       int n0, grp, x0, y0, b;
       decode(item, n0, grp, x0, y0, b);
       const int gx = x0 + tx;
@@ -255,8 +278,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const bool fuse_rgb = !UP && ep.rgb_out != nullptr;
       const float* wr = fuse_rgb ? ep.rgb_w + (long long)b * 3 * p.Cout : nullptr;
 #pragma unroll 1
-      for (int r = 0; r < p.R; ++r) {
-        float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+      for (int r = 0; r < ((p.dbg & 1) ? 0 : p.R); ++r) {
+        float2 rgb0 = make_float2(0.f, 0.f), rgb1 = rgb0, rgb2 = rgb0;
         const int gy = y0 + r * TH + ty;
         const bool in_grid = (gy < p.GH) && (gx < p.GW);
 #pragma unroll 1
@@ -279,7 +302,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const uint32_t acc_col = (uint32_t)(ph * p.R + r) * blk_cols;
 #pragma unroll 1
         for (int c = 0; c < p.BN; c += 16) {
-          if ((fuse_rgb ? r : (((ph * p.R + r) * p.BN + c) >> 4)) % EPI_GROUPS != egroup) continue;  // warp-uniform
+          if ((fuse_rgb ? job0 + r : (((ph * p.R + r) * p.BN + c) >> 4)) % EPI_GROUPS != egroup) continue;  // warp-uniform
           uint32_t rr[16];
           tmem_ld_x16(lane_addr + acc_col + (uint32_t)c, rr);
           if (p.cat) {
@@ -287,78 +310,99 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             tmem_ld_x16(lane_addr + acc_col + (uint32_t)(p.BN + c), r2);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
+            for (int i = 0; i < 8; ++i) {
+              const float2 t = fadd2(make_float2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1])),
+                                     make_float2(__uint_as_float(r2[2 * i]), __uint_as_float(r2[2 * i + 1])));
+              rr[2 * i] = __float_as_uint(t.x);
+              rr[2 * i + 1] = __float_as_uint(t.y);
+            }
           } else {
             tmem_ld_wait();
           }
           if (!valid) continue;
-          float v[16];
-          if (dptr) {
+          // Packed fp32 (fma/add/mul.rn.f32x2: two IEEE-rounded results per issue slot): the epilogue's instruction
+          // stream, not the tensor pipe, paced the Cout <= 128 layers (ncu: 263 SASS instructions per 16-column chunk,
+          // 160 of them scalar FADD/FMUL/FFMA) — the pairs below halve that part.
+          float2 v[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 dv = __ldg(reinterpret_cast<const float4*>(dptr + c) + q);
-              v[4 * q] = __uint_as_float(rr[4 * q]) * dv.x;
-              v[4 * q + 1] = __uint_as_float(rr[4 * q + 1]) * dv.y;
-              v[4 * q + 2] = __uint_as_float(rr[4 * q + 2]) * dv.z;
-              v[4 * q + 3] = __uint_as_float(rr[4 * q + 3]) * dv.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
-          }
+          for (int i = 0; i < 8; ++i) v[i] = make_float2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
           if (UP) {
-            float4* dst = reinterpret_cast<float4*>(ep.out_raw_nhwc + pix * p.Cout + n0 + c);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-            if (ep.activate) {
+            if (dptr) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ep.bias) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c) + q);
-                v[4 * q] = lrelu_s((v[4 * q] + nz) + bv.x, ep.slope, ep.act_scale);
-                v[4 * q + 1] = lrelu_s((v[4 * q + 1] + nz) + bv.y, ep.slope, ep.act_scale);
-                v[4 * q + 2] = lrelu_s((v[4 * q + 2] + nz) + bv.z, ep.slope, ep.act_scale);
-                v[4 * q + 3] = lrelu_s((v[4 * q + 3] + nz) + bv.w, ep.slope, ep.act_scale);
+                const float4 dv = __ldg(reinterpret_cast<const float4*>(dptr + c) + q);
+                v[2 * q] = fmul2(v[2 * q], make_float2(dv.x, dv.y));
+                v[2 * q + 1] = fmul2(v[2 * q + 1], make_float2(dv.z, dv.w));
+              }
+            }
+            float4* dst = reinterpret_cast<float4*>(ep.out_raw_nhwc + pix * p.Cout + n0 + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[2 * i].x, v[2 * i].y, v[2 * i + 1].x, v[2 * i + 1].y);
+          } else {
+            // o = lrelu(acc * d + noise + bias) * sqrt2: acc*d + noise as one FMA (one rounding less than the reference's
+            // separate multiply and add; the tensor-core path is tolerance-checked, 1e-3), then + bias
+            const float2 nz2 = make_float2(nz, nz);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 dv = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (dptr) dv = __ldg(reinterpret_cast<const float4*>(dptr + c) + q);
+              if (ep.activate && ep.bias) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c) + q);
+              v[2 * q] = ffma2(v[2 * q], make_float2(dv.x, dv.y), nz2);
+              v[2 * q + 1] = ffma2(v[2 * q + 1], make_float2(dv.z, dv.w), nz2);
+              if (ep.activate) {
+                v[2 * q] = fadd2(v[2 * q], make_float2(bv.x, bv.y));
+                v[2 * q + 1] = fadd2(v[2 * q + 1], make_float2(bv.z, bv.w));
+              }
+            }
+            if (ep.activate) {
+              const float2 sl2 = make_float2(ep.slope, ep.slope), sc2 = make_float2(ep.act_scale, ep.act_scale);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 t = fmul2(v[i], sl2);
+                v[i] = fmul2(make_float2(v[i].x > 0.f ? v[i].x : t.x, v[i].y > 0.f ? v[i].y : t.y), sc2);
               }
             }
             if (fuse_rgb) {
+              // three dot products over the tile's channels; (even, odd) channel partial sums ride in one register
+              // pair and are combined when the tile is stored (fixed order: deterministic)
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr + c) + q);
                 const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr + p.Cout + c) + q);
                 const float4 w2 = __ldg(reinterpret_cast<const float4*>(wr + 2 * p.Cout + c) + q);
-                rgb0 = fmaf(v[4 * q], w0.x, rgb0); rgb0 = fmaf(v[4 * q + 1], w0.y, rgb0);
-                rgb0 = fmaf(v[4 * q + 2], w0.z, rgb0); rgb0 = fmaf(v[4 * q + 3], w0.w, rgb0);
-                rgb1 = fmaf(v[4 * q], w1.x, rgb1); rgb1 = fmaf(v[4 * q + 1], w1.y, rgb1);
-                rgb1 = fmaf(v[4 * q + 2], w1.z, rgb1); rgb1 = fmaf(v[4 * q + 3], w1.w, rgb1);
-                rgb2 = fmaf(v[4 * q], w2.x, rgb2); rgb2 = fmaf(v[4 * q + 1], w2.y, rgb2);
-                rgb2 = fmaf(v[4 * q + 2], w2.z, rgb2); rgb2 = fmaf(v[4 * q + 3], w2.w, rgb2);
+                rgb0 = ffma2(v[2 * q], make_float2(w0.x, w0.y), rgb0);
+                rgb0 = ffma2(v[2 * q + 1], make_float2(w0.z, w0.w), rgb0);
+                rgb1 = ffma2(v[2 * q], make_float2(w1.x, w1.y), rgb1);
+                rgb1 = ffma2(v[2 * q + 1], make_float2(w1.z, w1.w), rgb1);
+                rgb2 = ffma2(v[2 * q], make_float2(w2.x, w2.y), rgb2);
+                rgb2 = ffma2(v[2 * q + 1], make_float2(w2.z, w2.w), rgb2);
               }
             }
             if (ep.out_f32_nchw) {
               float* dst = ep.out_f32_nchw + (((long long)b * p.Cout + n0 + c) * OH + oy) * OW + ox;
               const long long plane = (long long)OH * OW;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) dst[i * plane] = v[i];
+              for (int i = 0; i < 8; ++i) {
+                dst[(2 * i) * plane] = v[i].x;
+                dst[(2 * i + 1) * plane] = v[i].y;
+              }
             }
             if (ep.out_hi) {
               uint32_t h[8], l[8];
-              float sn[16];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 float4 sv = make_float4(1.f, 1.f, 1.f, 1.f);
                 if (ep.s_next) sv = __ldg(reinterpret_cast<const float4*>(ep.s_next + (long long)b * p.Cout + n0 + c) + q);
-                sn[4 * q] = sv.x; sn[4 * q + 1] = sv.y; sn[4 * q + 2] = sv.z; sn[4 * q + 3] = sv.w;
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float a0 = v[2 * i] * sn[2 * i], a1 = v[2 * i + 1] * sn[2 * i + 1];
-                const __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
-                const float2 hf = __bfloat1622float2(hh);
-                const __nv_bfloat162 ll = __floats2bfloat162_rn(a0 - hf.x, a1 - hf.y);
-                h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-                l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+                const float2 a01 = fmul2(v[2 * q], make_float2(sv.x, sv.y)), a23 = fmul2(v[2 * q + 1], make_float2(sv.z, sv.w));
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(a01.x, a01.y), h23 = __floats2bfloat162_rn(a23.x, a23.y);
+                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                const float2 neg1 = make_float2(-1.f, -1.f);
+                const float2 r01 = ffma2(f01, neg1, a01), r23 = ffma2(f23, neg1, a23);   // exact: a - hi
+                const __nv_bfloat162 l01 = __floats2bfloat162_rn(r01.x, r01.y), l23 = __floats2bfloat162_rn(r23.x, r23.y);
+                h[2 * q] = *reinterpret_cast<const uint32_t*>(&h01);
+                h[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                l[2 * q] = *reinterpret_cast<const uint32_t*>(&l01);
+                l[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&l23);
               }
               uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_hi) + pix * p.Cout + n0 + c);
               uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_lo) + pix * p.Cout + n0 + c);
@@ -370,12 +414,12 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           }
         }
         }
-        if (fuse_rgb && (r % EPI_GROUPS == egroup)) {
+        if (fuse_rgb && ((job0 + r) % EPI_GROUPS == egroup)) {
           const int gy2 = y0 + r * TH + ty;
           if (gy2 < p.H && gx < p.W) {
             float* o = ep.rgb_out + (((long long)b * 3) * p.H + gy2) * p.W + gx;
             const long long plane = (long long)p.H * p.W;
-            o[0] = rgb0; o[plane] = rgb1; o[2 * plane] = rgb2;
+            o[0] = rgb0.x + rgb0.y; o[plane] = rgb1.x + rgb1.y; o[2 * plane] = rgb2.x + rgb2.y;
           }
         }
       }
@@ -527,6 +571,8 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   if (items >= (1LL << 31)) return MAUA_E_UNSUPPORTED;
   p.n_items = (int)items;
   p.AS = (2 * blk_cols * R * p.n_phase <= 512) ? 2 : 1;
+  static const int dbg = [] { const char* e = getenv("MAUA_TC_DBG"); return e ? atoi(e) : 0; }();
+  p.dbg = dbg;
   cols = 32;
   while (cols < p.AS * blk_cols * R * p.n_phase) cols <<= 1;
   p.tmem_cols = (uint32_t)cols;
@@ -560,16 +606,21 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     ta_lo = ta_hi;
     tb_lo = tb_hi;
   }
-#define MAUA_TC2_LAUNCH(KCV, UPV)                                                                                   \
+#define MAUA_TC2_LAUNCH(KCV, UPV, MODEV)                                                                            \
   do {                                                                                                              \
     static size_t smem_set = 0; /* per instantiation; never called again during CUDA-graph capture */            \
     if (smem > smem_set) {                                                                                         \
-      MAUA_CHECK_CUDA(cudaFuncSetAttribute(modconv_tc2_kernel<KCV, UPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+      MAUA_CHECK_CUDA(cudaFuncSetAttribute(modconv_tc2_kernel<KCV, UPV, MODEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
       smem_set = smem;                                                                                             \
     }                                                                                                              \
-    modconv_tc2_kernel<KCV, UPV><<<(unsigned)grid, THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep);             \
+    modconv_tc2_kernel<KCV, UPV, MODEV><<<(unsigned)grid, THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep);      \
   } while (0)
-  if (up) MAUA_TC2_LAUNCH(32, true); else MAUA_TC2_LAUNCH(32, false);
+  const int mode = n_products == 1 ? 0 : (p.cat ? 2 : 1);
+  if (up) {
+    if (mode == 0) MAUA_TC2_LAUNCH(32, true, 0); else if (mode == 1) MAUA_TC2_LAUNCH(32, true, 1); else MAUA_TC2_LAUNCH(32, true, 2);
+  } else {
+    if (mode == 0) MAUA_TC2_LAUNCH(32, false, 0); else if (mode == 1) MAUA_TC2_LAUNCH(32, false, 1); else MAUA_TC2_LAUNCH(32, false, 2);
+  }
 #undef MAUA_TC2_LAUNCH
   MAUA_CHECK_LAUNCH("modconv_tc(v2)");
   return MAUA_OK;

@@ -17,6 +17,9 @@ ap.add_argument("--size", type=int, default=1024)
 ap.add_argument("--cm", type=int, default=2)
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--reps", type=int, default=8)
+ap.add_argument("--only", default=None, help="'cin,cout,h,up': run just this layer with the policy's configuration "
+                                             "(or --force 'R,BN,cat,groups'), no sweep — the ncu capture target")
+ap.add_argument("--force", default=None)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 chan = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * a.cm, 128: 128 * a.cm, 256: 64 * a.cm, 512: 32 * a.cm,
@@ -88,6 +91,14 @@ def run(cin, cout, h, up, fuse, last, force):
     torch.cuda.synchronize()
     return s.elapsed_time(e) / a.reps
 
+
+if a.only:
+    cin, cout, h, up = (int(v) for v in a.only.split(","))
+    force = tuple(int(v) for v in a.force.split(",")) if a.force else None
+    t = run(cin, cout, h, bool(up), (not up) and cout <= 128, (not up) and h == a.size, force)
+    print(f"{cin}->{cout} @{h} {'up' if up else 'same'} force={force}: {t:.4f} ms "
+          f"({2.0 * h * h * cin * cout * 9 * B / t / 1e9:.0f} TF/s)")
+    sys.exit(0)
 
 for cin, cout, h, up, fuse, last in layers:
     flops = 2.0 * h * h * cin * cout * 9 * B
