@@ -47,7 +47,8 @@ struct Params {
   int n_phase;           // accumulator phases per item: 1 same-res; transposed: 4 / 2 / 1 (4 / n_groups)
   int n_groups;          // transposed only: phase groups walked as separate work items (1, 2 or 4)
   int n_items;           // work items = n_tiles * tiles_x * tiles_y * B, walked with stride gridDim.x
-  int dbg;               // MAUA_TC_DBG (timing experiments, results invalid): 1 = empty epilogue, 2 = no A loads after the first
+  int dbg;               // MAUA_TC_DBG (timing experiments, results invalid): 1 = empty epilogue, 2 = no A loads after the
+                         // first, 4 = epilogue stops after the TMEM loads, 8 = epilogue without TMEM loads
 };
 
 // Tap lists.  same-res: tap (ky,kx) reads x[y+ky-1, x+kx-1] -> halo (ky, kx), one accumulator phase.
@@ -92,6 +93,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const uint32_t b_full = a_empty + 8 * p.SA, b_empty = b_full + 8 * p.SB;
   const uint32_t acc_full = b_empty + 8 * p.SB, acc_empty = acc_full + 8 * p.AS;
   const uint32_t tmem_slot = acc_empty + 8 * p.AS;
+  // per-sample epilogue vectors [d | bias | s_next | rgb w0 w1 w2], staged once per sample by the epilogue warps
+  float* const vec = reinterpret_cast<float*>(smem_raw + (((tmem_slot + 16u + 15u) & ~15u) - smem_u32(smem_raw)));
   // warp index through a shuffle: the compiler then KNOWS it is warp-uniform, so the role branches below are uniform
   // branches and loop state / descriptors of the single-role loops live in uniform registers (no R2UR per MMA)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -261,81 +264,126 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const float nwv = (!UP && ep.activate && ep.noise) ? __ldg(ep.noise_weight) : 0.f;
     int as = 0;
     uint32_t pacc = 0;
-    // fused ToRGB hands whole tiles to a warp (fixed summation order); tile r of the CTA's it-th item goes to epilogue
-    // group (it*R + r) % EPI_GROUPS, so that R = 2 / R = 4 items load the three groups evenly over consecutive items
-    // (a fixed r % EPI_GROUPS left one group idle for R = 2 and gave one group half of the work for R = 4)
+    // Hot-loop parameters pinned in registers: ptxas otherwise re-reads them from the constant bank inside the job loop
+    // and the LDC latency was 25 % of the epilogue's stall samples (ncu, 64->32 @512 up).
+    int R = p.R, BN = p.BN, Cout = p.Cout, n_phase = p.n_phase, GH = p.GH, GW = p.GW;
+    asm volatile("" : "+r"(R), "+r"(BN), "+r"(Cout), "+r"(n_phase), "+r"(GH), "+r"(GW));
+    const int bn16_log = 31 - __clz(BN >> 4), r_log = 31 - __clz(R);  // BN/16 and R are powers of two
+    const int nchunk = BN >> 4, ntile = n_phase * R;
+    const bool cat = p.cat != 0, act = ep.activate != 0;
+    // fused ToRGB (host guarantees BN == Cout): one warp owns all chunks of a tile so that the three dot products are
+    // summed in a fixed order; tile r of the CTA's it-th item goes to epilogue group (it*R + r) % EPI_GROUPS, so that
+    // R = 2 / R = 4 items load the three groups evenly over consecutive items.  Otherwise a job is one 16-column chunk
+    // of one accumulator, dealt round-robin.  Every warp walks only ITS jobs (no skip iterations).
+    const bool fuse_rgb = !UP && ep.rgb_out != nullptr;
+    const int OH = UP ? 2 * p.H + 1 : p.H, OW = UP ? 2 * p.W + 1 : p.W;
+    // Per-channel epilogue operands (demodulation d[b,:], bias, next-layer style s_next[b,:], ToRGB rows) are the same
+    // for every pixel of a sample.  Read through __ldg per 16-column chunk they cost 8-20 L1 round trips whose latency
+    // the three warps per scheduler cannot hide (ncu: long-scoreboard stalls on their first use = 45 % of the epilogue
+    // samples, plus spills from holding them across the TMEM wait).  They are staged in shared memory whenever the
+    // CTA's item sequence moves to another sample (batch is the slowest item coordinate: <= batch times per launch).
+    float* const sm_d = vec;
+    float* const sm_b = vec + Cout;
+    float* const sm_s = vec + 2 * Cout;
+    float* const sm_w = vec + 3 * Cout;
+    int cur_b = -1;
     int job0 = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, job0 = (job0 + p.R) % EPI_GROUPS) {
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, job0 = (job0 + R) % EPI_GROUPS) {
       int n0, grp, x0, y0, b;
       decode(item, n0, grp, x0, y0, b);
+      if (!UP && b != cur_b) {  // uniform over the epilogue warps: they all walk the same item sequence
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_GROUPS) : "memory");  // nobody still reads the old vectors
+        const int et = (int)threadIdx.x - 64;
+        for (int i = et; i < Cout; i += 128 * EPI_GROUPS) {
+          sm_d[i] = ep.d ? __ldg(ep.d + (long long)b * Cout + i) : 1.f;
+          sm_b[i] = (act && ep.bias) ? __ldg(ep.bias + i) : 0.f;
+          sm_s[i] = ep.s_next ? __ldg(ep.s_next + (long long)b * Cout + i) : 1.f;
+        }
+        if (fuse_rgb)
+          for (int i = et; i < 3 * Cout; i += 128 * EPI_GROUPS) sm_w[i] = __ldg(ep.rgb_w + (long long)b * 3 * Cout + i);
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_GROUPS) : "memory");
+        cur_b = b;
+      }
       const int gx = x0 + tx;
+      // Noise of this lane's pixel in each of the item's R tiles, requested BEFORE waiting for the accumulators: the
+      // noise map is streamed from HBM/L2 (4 B per pixel, no reuse), and with the load next to its use its ~1 us latency
+      // was the largest single stall of the same-resolution epilogue (ncu: 21 % of its samples on the consuming FMUL).
+      float nzv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!UP && act && ep.noise) {
+        const float* nrow = ep.noise + (long long)b * ep.noise_bstride + gx;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int gy = y0 + r * TH + ty;
+          if (r < R && gy < GH && gx < GW) nzv[r] = __ldg(nrow + (long long)gy * OW);
+        }
+      }
       mbar_wait(acc_full + 8 * as, pacc);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * acc_cols;
-      const float* dptr = ep.d ? ep.d + (long long)b * p.Cout + n0 : nullptr;
-      // fused ToRGB (host guarantees BN == Cout): one warp owns all chunks of a tile so that the three dot products
-      // are summed in a fixed (ascending channel) order
-      const bool fuse_rgb = !UP && ep.rgb_out != nullptr;
-      const float* wr = fuse_rgb ? ep.rgb_w + (long long)b * 3 * p.Cout : nullptr;
+      // (the transposed conv only needs d: 4 cached loads per chunk, issued before the TMEM load — measured faster than
+      // the shared-memory copy there, whose reads compete with the UMMA operand fetches of its busier tensor pipe)
+      const float* dglob = (UP && ep.d) ? ep.d + (long long)b * Cout + n0 : nullptr;
+      const float4* dptr = reinterpret_cast<const float4*>(sm_d + n0);
+      const float4* bptr = reinterpret_cast<const float4*>(sm_b + n0);
+      const float4* sptr = reinterpret_cast<const float4*>(sm_s + n0);
+      const int njobs = (p.dbg & 1) ? 0 : (fuse_rgb ? R : ntile * nchunk);
+      const int first_job = fuse_rgb ? (egroup + EPI_GROUPS - job0) % EPI_GROUPS : egroup;
 #pragma unroll 1
-      for (int r = 0; r < ((p.dbg & 1) ? 0 : p.R); ++r) {
-        float2 rgb0 = make_float2(0.f, 0.f), rgb1 = rgb0, rgb2 = rgb0;
+      for (int job = first_job; job < njobs; job += EPI_GROUPS) {
+        const int tile = fuse_rgb ? job : (job >> bn16_log);   // accumulator index = ph * R + r
+        const int ph = tile >> r_log, r = tile & (R - 1);
+        const int c_first = fuse_rgb ? 0 : ((job & (nchunk - 1)) << 4);
+        const int c_end = fuse_rgb ? BN : c_first + 16;
         const int gy = y0 + r * TH + ty;
-        const bool in_grid = (gy < p.GH) && (gx < p.GW);
-#pragma unroll 1
-        for (int ph = 0; ph < p.n_phase; ++ph) {
+        const bool in_grid = (gy < GH) && (gx < GW);
         // global sub-pixel phase (py, px) = (gph >> 1, gph & 1); two groups hold phases {0,3} and {1,2}
-        const int gph = !UP ? 0 : (p.n_groups == 2 ? (grp == 0 ? 3 * ph : 1 + ph) : grp * p.n_phase + ph);
-        int oy, ox, OH, OW;
-        bool valid;
-        if (UP) {
-          OH = 2 * p.H + 1; OW = 2 * p.W + 1;
-          oy = 2 * gy + (gph >> 1); ox = 2 * gx + (gph & 1);
-          valid = in_grid && oy < OH && ox < OW;
-        } else {
-          OH = p.H; OW = p.W; oy = gy; ox = gx; valid = in_grid;
-        }
+        const int gph = !UP ? 0 : (p.n_groups == 2 ? (grp == 0 ? 3 * ph : 1 + ph) : grp * n_phase + ph);
+        const int oy = UP ? 2 * gy + (gph >> 1) : gy, ox = UP ? 2 * gx + (gph & 1) : gx;
+        const bool valid = in_grid && oy < OH && ox < OW;
         const long long pix = valid ? (((long long)b * OH + oy) * OW + ox) : 0;
-        float nz = 0.f;
-        if (!UP && ep.activate && ep.noise && valid)
-          nz = nwv * __ldg(ep.noise + (long long)b * ep.noise_bstride + (long long)oy * OW + ox);
-        const uint32_t acc_col = (uint32_t)(ph * p.R + r) * blk_cols;
+        const float nz = UP ? 0.f : nwv * (r == 0 ? nzv[0] : (r == 1 ? nzv[1] : (r == 2 ? nzv[2] : nzv[3])));
+        const uint32_t acc_col = (uint32_t)tile * blk_cols;
+        float2 rgb0 = make_float2(0.f, 0.f), rgb1 = rgb0, rgb2 = rgb0;
 #pragma unroll 1
-        for (int c = 0; c < p.BN; c += 16) {
-          if ((fuse_rgb ? job0 + r : (((ph * p.R + r) * p.BN + c) >> 4)) % EPI_GROUPS != egroup) continue;  // warp-uniform
+        for (int c = c_first; c < c_end; c += 16) {   // a single iteration unless ToRGB is fused
+          float4 dup[4];
+          if (UP) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              dup[q] = dglob ? __ldg(reinterpret_cast<const float4*>(dglob + c) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
           uint32_t rr[16];
-          tmem_ld_x16(lane_addr + acc_col + (uint32_t)c, rr);
-          if (p.cat) {
+          if (p.dbg & 8) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rr[i] = (uint32_t)(c + i + lane);
+          } else {
+            tmem_ld_x16(lane_addr + acc_col + (uint32_t)c, rr);
+          }
+          float2 v[8];
+          if (cat && !(p.dbg & 8)) {
             uint32_t r2[16];
-            tmem_ld_x16(lane_addr + acc_col + (uint32_t)(p.BN + c), r2);
+            tmem_ld_x16(lane_addr + acc_col + (uint32_t)(BN + c), r2);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 t = fadd2(make_float2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1])),
-                                     make_float2(__uint_as_float(r2[2 * i]), __uint_as_float(r2[2 * i + 1])));
-              rr[2 * i] = __float_as_uint(t.x);
-              rr[2 * i + 1] = __float_as_uint(t.y);
-            }
+            for (int i = 0; i < 8; ++i)
+              v[i] = fadd2(make_float2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1])),
+                           make_float2(__uint_as_float(r2[2 * i]), __uint_as_float(r2[2 * i + 1])));
           } else {
             tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = make_float2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
           }
-          if (!valid) continue;
+          if (!valid || (p.dbg & 4)) continue;
           // Packed fp32 (fma/add/mul.rn.f32x2: two IEEE-rounded results per issue slot): the epilogue's instruction
           // stream, not the tensor pipe, paced the Cout <= 128 layers (ncu: 263 SASS instructions per 16-column chunk,
           // 160 of them scalar FADD/FMUL/FFMA) — the pairs below halve that part.
-          float2 v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = make_float2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
           if (UP) {
-            if (dptr) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 dv = __ldg(reinterpret_cast<const float4*>(dptr + c) + q);
-                v[2 * q] = fmul2(v[2 * q], make_float2(dv.x, dv.y));
-                v[2 * q + 1] = fmul2(v[2 * q + 1], make_float2(dv.z, dv.w));
-              }
+            for (int q = 0; q < 4; ++q) {
+              v[2 * q] = fmul2(v[2 * q], make_float2(dup[q].x, dup[q].y));
+              v[2 * q + 1] = fmul2(v[2 * q + 1], make_float2(dup[q].z, dup[q].w));
             }
-            float4* dst = reinterpret_cast<float4*>(ep.out_raw_nhwc + pix * p.Cout + n0 + c);
+            float4* dst = reinterpret_cast<float4*>(ep.out_raw_nhwc + pix * Cout + n0 + c);
 #pragma unroll
             for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[2 * i].x, v[2 * i].y, v[2 * i + 1].x, v[2 * i + 1].y);
           } else {
@@ -344,17 +392,16 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             const float2 nz2 = make_float2(nz, nz);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              float4 dv = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (dptr) dv = __ldg(reinterpret_cast<const float4*>(dptr + c) + q);
-              if (ep.activate && ep.bias) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + c) + q);
+              const float4 dv = dptr[(c >> 2) + q];
               v[2 * q] = ffma2(v[2 * q], make_float2(dv.x, dv.y), nz2);
               v[2 * q + 1] = ffma2(v[2 * q + 1], make_float2(dv.z, dv.w), nz2);
-              if (ep.activate) {
+              if (act) {
+                const float4 bv = bptr[(c >> 2) + q];
                 v[2 * q] = fadd2(v[2 * q], make_float2(bv.x, bv.y));
                 v[2 * q + 1] = fadd2(v[2 * q + 1], make_float2(bv.z, bv.w));
               }
             }
-            if (ep.activate) {
+            if (act) {
               const float2 sl2 = make_float2(ep.slope, ep.slope), sc2 = make_float2(ep.act_scale, ep.act_scale);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -367,9 +414,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               // pair and are combined when the tile is stored (fixed order: deterministic)
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr + c) + q);
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr + p.Cout + c) + q);
-                const float4 w2 = __ldg(reinterpret_cast<const float4*>(wr + 2 * p.Cout + c) + q);
+                const float4 w0 = reinterpret_cast<const float4*>(sm_w + c)[q];
+                const float4 w1 = reinterpret_cast<const float4*>(sm_w + Cout + c)[q];
+                const float4 w2 = reinterpret_cast<const float4*>(sm_w + 2 * Cout + c)[q];
                 rgb0 = ffma2(v[2 * q], make_float2(w0.x, w0.y), rgb0);
                 rgb0 = ffma2(v[2 * q + 1], make_float2(w0.z, w0.w), rgb0);
                 rgb1 = ffma2(v[2 * q], make_float2(w1.x, w1.y), rgb1);
@@ -379,7 +426,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               }
             }
             if (ep.out_f32_nchw) {
-              float* dst = ep.out_f32_nchw + (((long long)b * p.Cout + n0 + c) * OH + oy) * OW + ox;
+              float* dst = ep.out_f32_nchw + (((long long)b * Cout + n0 + c) * OH + oy) * OW + ox;
               const long long plane = (long long)OH * OW;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -391,8 +438,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               uint32_t h[8], l[8];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                float4 sv = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (ep.s_next) sv = __ldg(reinterpret_cast<const float4*>(ep.s_next + (long long)b * p.Cout + n0 + c) + q);
+                const float4 sv = sptr[(c >> 2) + q];
                 const float2 a01 = fmul2(v[2 * q], make_float2(sv.x, sv.y)), a23 = fmul2(v[2 * q + 1], make_float2(sv.z, sv.w));
                 const __nv_bfloat162 h01 = __floats2bfloat162_rn(a01.x, a01.y), h23 = __floats2bfloat162_rn(a23.x, a23.y);
                 const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
@@ -404,8 +450,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 l[2 * q] = *reinterpret_cast<const uint32_t*>(&l01);
                 l[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&l23);
               }
-              uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_hi) + pix * p.Cout + n0 + c);
-              uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_lo) + pix * p.Cout + n0 + c);
+              uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_hi) + pix * Cout + n0 + c);
+              uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_lo) + pix * Cout + n0 + c);
               dh[0] = make_uint4(h[0], h[1], h[2], h[3]);
               dh[1] = make_uint4(h[4], h[5], h[6], h[7]);
               dl[0] = make_uint4(l[0], l[1], l[2], l[3]);
@@ -413,14 +459,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             }
           }
         }
-        }
-        if (fuse_rgb && ((job0 + r) % EPI_GROUPS == egroup)) {
-          const int gy2 = y0 + r * TH + ty;
-          if (gy2 < p.H && gx < p.W) {
-            float* o = ep.rgb_out + (((long long)b * 3) * p.H + gy2) * p.W + gx;
-            const long long plane = (long long)p.H * p.W;
-            o[0] = rgb0.x + rgb0.y; o[plane] = rgb1.x + rgb1.y; o[2 * plane] = rgb2.x + rgb2.y;
-          }
+        if (fuse_rgb && gy < p.H && gx < p.W) {
+          float* o = ep.rgb_out + (((long long)b * 3) * p.H + gy) * p.W + gx;
+          const long long plane = (long long)p.H * p.W;
+          o[0] = rgb0.x + rgb0.y; o[plane] = rgb1.x + rgb1.y; o[2 * plane] = rgb2.x + rgb2.y;
         }
       }
       // accumulator stage drained: hand it back to the MMA issuer
@@ -460,7 +502,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   // Persistent kernel: one CTA per SM owns the whole shared memory (deep rings) and all 512 TMEM columns; when two
   // accumulator stages fit (2*R*nphase*BN <= 512) the epilogue of item i overlaps the MMAs of item i+1.
   const int tmem_cap = 512;
-  const uint32_t budget = 212u * 1024u;
+  const uint32_t budget = 212u * 1024u - 6u * (uint32_t)cout * 4u;  // minus the epilogue's per-sample vectors
   // Configuration (R stacked tiles, BN, concat mode, phase groups).  tools/tune_tc2.py sweeps the whole space on
   // hardware; across config-f 1024^2 (batch 2 and 8) and config-e 512^2 the winner only depends on Cout and on the
   // layer kind -- widest N first (a 128 x N x 16 MMA fetches its 4 KB A tile from shared memory whatever N is, so
@@ -565,7 +607,8 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   else if (sb > 12) sb = 12;
   if (sb < 2) return unsupported;
   p.SB = sb;
-  const size_t smem = (size_t)p.SA * a_stage + (size_t)p.SB * b_stage + 8 * (2 * p.SA + 2 * p.SB + 6) + 1024;
+  const size_t smem = (size_t)p.SA * a_stage + (size_t)p.SB * b_stage + 8 * (2 * p.SA + 2 * p.SB + 6) + 1024 +
+                      6 * (size_t)cout * 4 + 32;
   if (smem > 227 * 1024) return unsupported;
   const long long items = tiles_x * p.tiles_y * batch * p.n_tiles * p.n_groups;
   if (items >= (1LL << 31)) return MAUA_E_UNSUPPORTED;
