@@ -507,8 +507,10 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   // hardware; across config-f 1024^2 (batch 2 and 8) and config-e 512^2 the winner only depends on Cout and on the
   // layer kind -- widest N first (a 128 x N x 16 MMA fetches its 4 KB A tile from shared memory whatever N is, so
   // small-N MMAs are operand-fetch bound), two accumulator stages where TMEM allows:
-  //     same-res:  Cout>=256 (1,256)   128 (2,128)   64 (2,64)   <=32 (4,Cout,concat)
-  //     up:        Cout>=256 (1,256, 4 groups)   128 (1,128, 2 groups)   64 (2,64, 2 groups)   <=32 (2,Cout)
+  //     same-res:  Cout>=256 (1,256)   128 (2,128)   64 (1,64,concat)   <=32 (4,Cout,concat)
+  //     up:        Cout>=256 (1,256, 4 groups)   128 (1,128, 2 groups)   64 (2,64, 2 groups)   <=32 (1,Cout,concat)
+  // (re-measured after the issue-loop / epilogue rework of this round: the concat product now also wins for Cout = 64
+  // same-res and for the Cout <= 32 transposed layers)
   // The search below (cost model) only decides when the preferred configuration is infeasible or leaves most SMs idle.
   int best_r = 0, best_bn = 0, best_cat = 0, best_groups = 1;
   static const int force_groups = [] { const char* e = getenv("MAUA_TC_GROUPS"); return e ? atoi(e) : 0; }();
@@ -565,8 +567,8 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     int pr, pbn, pcat = 0, pg = 1;
     if (cout >= 256) { pr = 1; pbn = 256; pg = up ? 4 : 1; }
     else if (cout == 128) { pr = up ? 1 : 2; pbn = 128; pg = up ? 2 : 1; }
-    else if (cout == 64) { pr = 2; pbn = 64; pg = up ? 2 : 1; }
-    else { pr = up ? 2 : 4; pbn = cout; pcat = up ? 0 : 1; }
+    else if (cout == 64) { pr = up ? 2 : 1; pbn = 64; pg = up ? 2 : 1; pcat = up ? 0 : 1; }
+    else { pr = up ? 1 : 4; pbn = cout; pcat = 1; }
     if (force_groups && up) pg = force_groups;
     while (pr > 1 && pr > rows16) pr >>= 1;
     // keep (most of) the 148 SMs busy: first fewer stacked tiles, then more phase groups, then narrower N
