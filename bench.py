@@ -228,7 +228,21 @@ def cpu_model():
 
 
 # ----------------------------------------------------------------------------------------------------------------
+def _emit(line):
+    """The ONE JSON line on the real stdout (see main(): fd 1 is pointed at stderr while the bench runs)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    # Libraries print to stdout behind Python's back (NCCL: "NCCL version 2.28.9+cuda12.9" on the first collective);
+    # the contract is ONE JSON line, so everything else written to fd 1 is sent to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -260,7 +274,7 @@ def main():
                                  "sample": r["sample"], "cpu": cpu_model()},
                 "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        _emit(line)
         return
 
     import torch
@@ -438,7 +452,7 @@ def main():
                 "gpu_launches": int(lt.item()), "roofline": roof, "roofline_upfirdn2d": roof_ufd,
                 "kernel_ms_per_step": shares, "cpu_baseline": cpu,
                 "conv_gflop_per_frame": CONV_GFLOP_PER_FRAME}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
