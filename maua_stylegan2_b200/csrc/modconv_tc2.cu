@@ -491,7 +491,15 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
                        cudaStream_t st) {
   using namespace tc2;
   const int GH = up ? h + 1 : h, GW = up ? w + 1 : w;
-  if (GH < 4 * TH || GW < 4 * TW) return MAUA_E_UNSUPPORTED;  // <= 32^2 (measured): v1's batch-folded tiles are faster
+  // <= 32^2 (measured): v1's batch-folded tiles are faster — except the same-resolution Cout >= 256 layer at 32^2 once
+  // the batch fills the machine with (R=1, BN=256) items (512->512 @32^2, batch 8: 0.088 ms vs 0.103 ms for v1).
+  // MAUA_TC2_MIN_TILES overrides the threshold (experiments).
+  static const int min_tiles = [] { const char* e = getenv("MAUA_TC2_MIN_TILES"); return e ? atoi(e) : 4; }();
+  if (GH < min_tiles * TH || GW < min_tiles * TW) {
+    const bool wide32 = !up && GH >= 2 * TH && GW >= 2 * TW && cout >= 256 && cout % 256 == 0 &&
+                        (long long)ceil_div(GW, TW) * ceil_div(GH, TH) * batch * (cout / 256) >= 120;
+    if (!wide32) return MAUA_E_UNSUPPORTED;
+  }
   Params p;
   p.B = batch; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout; p.GH = GH; p.GW = GW;
   const int nphase = up ? 4 : 1;

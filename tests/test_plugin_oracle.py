@@ -71,3 +71,53 @@ def test_bend_oracle_identity_zoom_and_rotation():
     assert torch.allclose(P.rotate(x, torch.zeros(2), 6, 6), x, atol=1e-5)
     r90 = P.rotate(x, torch.full((2,), 90.0), 6, 6)
     assert torch.allclose(r90, torch.rot90(x, 1, (2, 3)), atol=1e-4)  # positive angle = anti-clockwise
+
+
+def test_spline_weight_matrix_reproduces_reference_spline_loops():
+    """Host logic of the product's spline_loops: the FITPACK-equivalent basis matrix times the selection == the reference's
+    per-coordinate splrep/splev (golden), for both the looped (5 knots) and open (4 knots) case."""
+    from maua_stylegan2_b200.audioreactive.latent import spline_weights
+
+    sel = G["spline_sel"].astype(np.float64)
+    loop = np.concatenate([sel, sel[[0]]])
+    y = np.einsum("tn,nld->tld", spline_weights(5, 50), loop)
+    assert np.abs(y - G["spline_y_100_2"][:50]).max() <= 1e-12
+    assert np.array_equal(G["spline_y_100_2"][:50], G["spline_y_100_2"][50:])
+    y = np.einsum("tn,nld->tld", spline_weights(4, 32), sel)
+    assert np.abs(y - G["spline_y_97_3_noloop"][:32]).max() <= 1e-12
+    with pytest.raises(ValueError):
+        spline_weights(3, 10)
+
+
+def test_log_filterbank_host_table_matches_oracle():
+    """madmom-flavoured onsets: the product's filterbank table (host side) against the oracle restatement, and the band
+    ranges the ComplexFlux mask kernel reads."""
+    from maua_stylegan2_b200.audioreactive import filters
+    from oracle import audio_oracle as A
+
+    for sr, fmin, fmax in ((22050, 20, 8000), (44100, 20, 150), (44100, 500, 8000), (48000, 30, 17000)):
+        fb, lo, hi = filters.log_filterbank(sr, 1024, 24, fmin, fmax)
+        ref = A.mm_log_filterbank(sr, 1024, 24, fmin, fmax)
+        assert fb.shape == ref.T.shape and np.array_equal(fb.T, ref)
+        np.testing.assert_allclose(fb.sum(1), 1.0, atol=1e-5)            # norm_filters=True
+        for b in range(fb.shape[0]):
+            nz = np.nonzero(fb[b])[0]
+            assert lo[b] == max(nz[0] - 1, 0) and hi[b] == min(nz[-1] + 2, 1024)
+
+
+def test_madmom_onset_oracle_reacts_to_clicks():
+    """Sanity of the restated detection functions: a click train produces peaks at the click frames."""
+    from oracle import audio_oracle as A
+
+    sr = 22050
+    y = np.zeros(sr * 2, np.float32)
+    clicks = [0.5, 1.0, 1.5]
+    rng = np.random.Generator(np.random.PCG64(0))
+    for c in clicks:
+        i = int(c * sr)
+        y[i:i + 200] += rng.standard_normal(200).astype(np.float32) * np.hanning(200).astype(np.float32)
+    o = A.onset_strength_mm(y, sr, 20, 8000)
+    assert o.shape == (int(np.ceil(len(y) / 441)),)
+    peaks = sorted(np.argsort(o)[-3:])
+    want = [int(round(c * sr / 441)) for c in clicks]
+    assert all(abs(p - w) <= 3 for p, w in zip(peaks, want)), (peaks, want)
