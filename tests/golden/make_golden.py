@@ -192,6 +192,13 @@ def plugin_cases(ar):
     out["slerp_a"], out["slerp_b"] = a, b
     out["slerp_y"] = np.stack([ar.slerp(v, a, b) for v in (0.0, 0.25, 0.5, 1.0)])
     out["slerp_same"] = ar.slerp(0.3, a, a)
+    # generate_audiovisual.get_noise_range (generate_audiovisual.py:22-34): which noise scales get_noise is asked for
+    import generate_audiovisual as ref_ga
+
+    for o, g in ((1024, 1024), (1920, 1024), (1080, 1024), (512, 512), (1024, 512), (1920, 512), (512, 256)):
+        for sg1 in (False, True):
+            lo, hi, f = ref_ga.get_noise_range(o, g, sg1)
+            out[f"noise_range_{o}_{g}_{int(sg1)}"] = np.array([lo, hi] + [f(s) for s in range(lo, hi)])
     t = torch.arange(10)
     out["wrap_8_5"] = ar.wrapping_slice(t, 8, 5).numpy()
     out["wrap_2_4"] = ar.wrapping_slice(t, 2, 4).numpy()

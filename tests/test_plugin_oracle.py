@@ -121,3 +121,16 @@ def test_madmom_onset_oracle_reacts_to_clicks():
     peaks = sorted(np.argsort(o)[-3:])
     want = [int(round(c * sr / 441)) for c in clicks]
     assert all(abs(p - w) <= 3 for p, w in zip(peaks, want)), (peaks, want)
+
+
+def test_get_noise_range_matches_reference():
+    """generate_audiovisual.get_noise_range (generate_audiovisual.py:22-34) decides which (height, width) get_noise is
+    called with; golden values come from the reference function itself."""
+    from maua_stylegan2_b200.generate_audiovisual import get_noise_range
+
+    keys = [k for k in G.files if k.startswith("noise_range_")]
+    assert len(keys) == 14
+    for k in keys:
+        o, g, sg1 = (int(v) for v in k.split("_")[2:])
+        lo, hi, f = get_noise_range(o, g, bool(sg1))
+        assert [lo, hi] + [f(s) for s in range(lo, hi)] == list(G[k]), k
