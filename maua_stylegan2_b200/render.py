@@ -13,6 +13,7 @@ What changed underneath (SURVEY.md §2.1 "D2H + uint8 convert", §3.2):
   * no 5-second `queue.get` timeouts: the writer is a plain bounded queue + thread that cannot silently truncate
     the video when a batch is slow (render.py:37,97 hazard).
 """
+import os
 import queue
 import subprocess
 import threading
@@ -281,12 +282,16 @@ class FramePipeline:
 class FFmpegSink:
     """rawvideo rgb24 on stdin -> libx264 yuv420p (+ 320k audio mux), the reference's wire format (render.py:58-91)."""
 
-    def __init__(self, output_file, width, height, fps, audio_file=None, offset=0, duration=None, preset="slow"):
+    def __init__(self, output_file, width, height, fps, audio_file=None, offset=0, duration=None, preset="slow",
+                 vcodec=None):
+        # libx264 like the reference; MAUA_VCODEC=h264_nvenc (or vcodec=) hands the encode to NVENC when the installed
+        # ffmpeg was built with it — at >1000 frames/s of synthesis libx264 `slow` is the end-to-end limit (SURVEY §8(f) 2)
+        vcodec = vcodec or os.environ.get("MAUA_VCODEC", "libx264")
         cmd = ["ffmpeg", "-hide_banner", "-y", "-v", "warning", "-f", "rawvideo", "-pix_fmt", "rgb24", "-framerate",
                str(fps), "-s", f"{width}x{height}", "-i", "pipe:"]
         if audio_file is not None:
             cmd += ["-ss", str(offset)] + (["-t", str(duration)] if duration else []) + ["-i", audio_file]
-        cmd += ["-framerate", str(fps), "-vcodec", "libx264", "-pix_fmt", "yuv420p", "-preset", preset]
+        cmd += ["-framerate", str(fps), "-vcodec", vcodec, "-pix_fmt", "yuv420p", "-preset", preset]
         if audio_file is not None:
             cmd += ["-b:a", "320K", "-ac", "2"]
         cmd += [output_file]
