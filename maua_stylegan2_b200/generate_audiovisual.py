@@ -66,130 +66,133 @@ def load_hooks(audioreactive_file):
     return funcs, dict(getattr(mod, "OVERRIDE", {}))
 
 
+def _namespace(values, skip):
+    """`args` as the reference builds it: every keyword of generate() as an attribute (generate_audiovisual.py:93-98)."""
+    ns = argparse.Namespace()
+    for key, value in values.items():
+        if key not in skip:
+            setattr(ns, key, value)
+    return ns
+
+
+def _audio_and_frames(args, audio, audio_file, offset, duration, fps):
+    """Decode (or take) the audio, fix duration / n_frames and publish them on `args` (:103-108)."""
+    if audio is None:
+        samples, sr, duration = ar.load_audio(audio_file, offset, duration)
+    else:
+        samples, sr = audio
+        if duration == -1:
+            duration = len(samples) / sr
+    args.audio, args.sr, args.duration = samples, sr, duration
+    args.n_frames = int(round(duration * fps))
+    return duration
+
+
+def _noise_maps(get_noise, args, out_size, G_res, stylegan1):
+    """One get_noise call per noise input of the generator, coarse to fine (:149-157); 1920 / 1080 outputs double the
+    width / height of every map."""
+    first, last, to_log2 = get_noise_range(out_size, G_res, stylegan1)
+    tall, wide = (2 if out_size == 1080 else 1), (2 if out_size == 1920 else 1)
+    maps = []
+    for scale in range(first, last):
+        edge = 2 ** to_log2(scale)
+        m = get_noise(height=tall * edge, width=wide * edge, scale=scale - first, num_scales=last - first, args=args)
+        if m is not None:
+            print(list(m.shape), f"amplitude={m.std()}")
+        maps.append(m)
+    return maps
+
+
 def generate(ckpt, audio_file, initialize=None, get_latents=None, get_noise=None, get_bends=None, get_rewrites=None,
              get_truncation=None, output_dir="./output", audioreactive_file=DEFAULT_HOOK_FILE, offset=0, duration=-1,
              latent_file=None, shuffle_latents=False, G_res=1024, out_size=1024, fps=30, latent_count=12, batch=8,
              dataparallel=False, truncation=1.0, stylegan1=False, noconst=False, latent_dim=512, n_mlp=8,
              channel_multiplier=2, randomize_noise=False, ffmpeg_preset="slow", base_res_factor=1, output_file=None,
              args=None, audio=None, sink=None, generator=None, latent_selection=None):
+    started = time.time()
     if args is None:
-        kwargs = dict(locals())
-        args = argparse.Namespace()
-        for k, v in kwargs.items():
-            if k not in ("audio", "sink", "generator", "latent_selection", "kwargs"):
-                setattr(args, k, v)
-
-    ar.set_SMF(fps / 30)  # smoothing independent of frame rate (:101)
-    time_taken = time.time()
+        args = _namespace(dict(locals()), skip=("audio", "sink", "generator", "latent_selection", "started"))
+    ar.set_SMF(fps / 30)  # smoothing independent of the frame rate (:101)
     th.set_grad_enabled(False)
+    duration = _audio_and_frames(args, audio, audio_file, offset, duration, fps)
 
-    if audio is not None:
-        audio_arr, sr = audio
-        duration = len(audio_arr) / sr if duration == -1 else duration
-    else:
-        audio_arr, sr, duration = ar.load_audio(audio_file, offset, duration)
-    args.audio, args.sr = audio_arr, sr
-    n_frames = int(round(duration * fps))
-    args.duration, args.n_frames = duration, n_frames
-
-    default_funcs = None
+    # hooks that were not supplied fall back to the shipped default hook file
+    fallback = None
     if get_latents is None or get_noise is None:
-        default_funcs, _ = load_hooks(DEFAULT_HOOK_FILE)
+        fallback, _ = load_hooks(DEFAULT_HOOK_FILE)
         if initialize is None and get_latents is None:
-            initialize = default_funcs["initialize"]
+            initialize = fallback["initialize"]
+        get_latents = get_latents or fallback["get_latents"]
+        get_noise = get_noise or fallback["get_noise"]
     if initialize is not None:
         args = initialize(args)
 
-    # ---- latents ---------------------------------------------------------------------------------------------------
-    if get_latents is None:
-        get_latents = default_funcs["get_latents"]
     if latent_selection is None:
-        if latent_file is not None:
-            latent_selection = ar.load_latents(latent_file)
-        else:
-            latent_selection = ar.generate_latents(latent_count, ckpt, G_res, noconst, latent_dim, n_mlp, channel_multiplier)
+        latent_selection = (ar.load_latents(latent_file) if latent_file is not None else
+                            ar.generate_latents(latent_count, ckpt, G_res, noconst, latent_dim, n_mlp, channel_multiplier))
     if shuffle_latents:
-        idx = random.sample(range(len(latent_selection)), len(latent_selection))
-        latent_selection = latent_selection[idx]
+        latent_selection = latent_selection[random.sample(range(len(latent_selection)), len(latent_selection))]
     latents = get_latents(selection=latent_selection, args=args)
     print(f"{list(latents.shape)} amplitude={latents.std()}\n")
 
-    # ---- noise -----------------------------------------------------------------------------------------------------
-    if get_noise is None:
-        get_noise = default_funcs["get_noise"]
-    noise = []
-    range_min, range_max, exponent = get_noise_range(out_size, G_res, stylegan1)
-    for scale in range(range_min, range_max):
-        h = (2 if out_size == 1080 else 1) * 2 ** exponent(scale)
-        w = (2 if out_size == 1920 else 1) * 2 ** exponent(scale)
-        noise.append(get_noise(height=h, width=w, scale=scale - range_min, num_scales=range_max - range_min, args=args))
-        if noise[-1] is not None:
-            print(list(noise[-1].shape), f"amplitude={noise[-1].std()}")
+    noise = _noise_maps(get_noise, args, out_size, G_res, stylegan1)
     gc.collect()
-
-    bends = get_bends(args=args) if get_bends is not None else []
-    rewrites = get_rewrites(args=args) if get_rewrites is not None else {}
-    truncation = get_truncation(args=args) if get_truncation is not None else float(truncation)
+    bends = [] if get_bends is None else get_bends(args=args)
+    rewrites = {} if get_rewrites is None else get_rewrites(args=args)
+    truncation = float(truncation) if get_truncation is None else get_truncation(args=args)
 
     if generator is None:
         generator = load_generator(ckpt, stylegan1, G_res, out_size, noconst, latent_dim, n_mlp, channel_multiplier,
                                    dataparallel, base_res_factor)
-    print(f"\npreprocessing took {time.time() - time_taken:.2f}s\n")
-    print(f"rendering {n_frames} frames...")
+    print(f"\npreprocessing took {time.time() - started:.2f}s\n")
+    print(f"rendering {args.n_frames} frames...")
     if output_file is None and sink is None:
         os.makedirs(output_dir, exist_ok=True)
-        checkpoint_title = str(ckpt).split("/")[-1].split(".")[0].lower()
-        track_title = str(audio_file).split("/")[-1].split(".")[0].lower()
-        output_file = f"{output_dir}/{track_title}_{checkpoint_title}_{uuid.uuid4().hex[:8]}.mp4"
+        stem = lambda path: str(path).split("/")[-1].split(".")[0].lower()
+        output_file = f"{output_dir}/{stem(audio_file)}_{stem(ckpt)}_{uuid.uuid4().hex[:8]}.mp4"
     pipe = render.render(generator=generator, latents=latents, noise=noise, audio_file=audio_file, offset=offset,
                          duration=duration, batch_size=batch, truncation=truncation, bends=bends, rewrites=rewrites,
                          out_size=out_size, output_file=output_file, randomize_noise=randomize_noise,
                          ffmpeg_preset=ffmpeg_preset, sink=sink)
-    print(f"\ntotal time taken: {(time.time() - time_taken) / 60:.2f} minutes")
+    print(f"\ntotal time taken: {(time.time() - started) / 60:.2f} minutes")
     return pipe
 
 
-def main():
-    parser = argparse.ArgumentParser()
-    parser.add_argument("--ckpt", type=str)
-    parser.add_argument("--audio_file", type=str)
-    parser.add_argument("--audioreactive_file", type=str, default=DEFAULT_HOOK_FILE)
-    parser.add_argument("--output_dir", type=str, default="./output")
-    parser.add_argument("--offset", type=float, default=0)
-    parser.add_argument("--duration", type=float, default=-1)
-    parser.add_argument("--latent_file", type=str, default=None)
-    parser.add_argument("--shuffle_latents", action="store_true")
-    parser.add_argument("--G_res", type=int, default=1024)
-    parser.add_argument("--out_size", type=int, default=1024)
-    parser.add_argument("--fps", type=int, default=30)
-    parser.add_argument("--latent_count", type=int, default=12)
-    parser.add_argument("--batch", type=int, default=8)
-    parser.add_argument("--dataparallel", action="store_true")
-    parser.add_argument("--truncation", type=float, default=1.0)
-    parser.add_argument("--stylegan1", action="store_true")
-    parser.add_argument("--noconst", action="store_true")
-    parser.add_argument("--latent_dim", type=int, default=512)
-    parser.add_argument("--n_mlp", type=int, default=8)
-    parser.add_argument("--channel_multiplier", type=int, default=2)
-    parser.add_argument("--randomize_noise", action="store_true")
-    parser.add_argument("--base_res_factor", type=float, default=1)
-    parser.add_argument("--ffmpeg_preset", type=str, default="slow")
-    parser.add_argument("--output_file", type=str, default=None)
-    args = parser.parse_args()
+# CLI flags 1:1 with the reference (generate_audiovisual.py:235-260): (flag, type or None for a switch, default)
+CLI_FLAGS = [
+    ("ckpt", str, None), ("audio_file", str, None), ("audioreactive_file", str, DEFAULT_HOOK_FILE),
+    ("output_dir", str, "./output"), ("offset", float, 0), ("duration", float, -1), ("latent_file", str, None),
+    ("shuffle_latents", None, False), ("G_res", int, 1024), ("out_size", int, 1024), ("fps", int, 30),
+    ("latent_count", int, 12), ("batch", int, 8), ("dataparallel", None, False), ("truncation", float, 1.0),
+    ("stylegan1", None, False), ("noconst", None, False), ("latent_dim", int, 512), ("n_mlp", int, 8),
+    ("channel_multiplier", int, 2), ("randomize_noise", None, False), ("base_res_factor", float, 1),
+    ("ffmpeg_preset", str, "slow"), ("output_file", str, None),
+]
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description="audio-reactive StyleGAN2 video on the B200 path")
+    for flag, kind, default in CLI_FLAGS:
+        if kind is None:
+            parser.add_argument(f"--{flag}", action="store_true")
+        else:
+            parser.add_argument(f"--{flag}", type=kind, default=default)
+    return parser
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
     os.makedirs(args.output_dir, exist_ok=True)
     try:
-        funcs, override = load_hooks(args.audioreactive_file)
+        hooks, override = load_hooks(args.audioreactive_file)
     except Exception:
         print("Error while loading --audioreactive_file...")
         traceback.print_exc()
         raise SystemExit(1)
-    arg_dict = vars(args).copy()
-    for k, v in override.items():
-        arg_dict[k] = v
-        setattr(args, k, v)
-    ckpt = arg_dict.pop("ckpt", None)
-    audio_file = arg_dict.pop("audio_file", None)
-    generate(ckpt=ckpt, audio_file=audio_file, **funcs, **arg_dict, args=args)
+    for key, value in override.items():  # the hook file's OVERRIDE dict wins over the command line (:284-292)
+        setattr(args, key, value)
+    kwargs = vars(args).copy()
+    generate(ckpt=kwargs.pop("ckpt", None), audio_file=kwargs.pop("audio_file", None), **hooks, **kwargs, args=args)
 
 
 if __name__ == "__main__":
