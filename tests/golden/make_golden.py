@@ -199,6 +199,20 @@ def plugin_cases(ar):
         for sg1 in (False, True):
             lo, hi, f = ref_ga.get_noise_range(o, g, sg1)
             out[f"noise_range_{o}_{g}_{int(sg1)}"] = np.array([lo, hi] + [f(s) for s in range(lo, hi)])
+    # plugin surface: generate() parameters + defaults (generate_audiovisual.py:59-91) and the CLI flags (:235-260)
+    import ast
+    import inspect
+    import json
+
+    sig = inspect.signature(ref_ga.generate)
+    out["generate_signature"] = np.array(json.dumps(
+        [[n, None if p.default is inspect.Parameter.empty else repr(p.default)] for n, p in sig.parameters.items()]))
+    flags = []
+    for node in ast.walk(ast.parse(open(os.path.join(REF, "generate_audiovisual.py")).read())):
+        if isinstance(node, ast.Call) and getattr(node.func, "attr", "") == "add_argument":
+            kw = {k.arg: ast.literal_eval(k.value) if not isinstance(k.value, ast.Name) else k.value.id for k in node.keywords}
+            flags.append([node.args[0].value, kw.get("type"), kw.get("default"), kw.get("action")])
+    out["cli_flags"] = np.array(json.dumps(flags))
     t = torch.arange(10)
     out["wrap_8_5"] = ar.wrapping_slice(t, 8, 5).numpy()
     out["wrap_2_4"] = ar.wrapping_slice(t, 2, 4).numpy()

@@ -134,3 +134,54 @@ def test_get_noise_range_matches_reference():
         o, g, sg1 = (int(v) for v in k.split("_")[2:])
         lo, hi, f = get_noise_range(o, g, bool(sg1))
         assert [lo, hi] + [f(s) for s in range(lo, hi)] == list(G[k]), k
+
+
+def test_plugin_surface_matches_reference():
+    """generate() parameters (names, order, defaults) and the CLI flags are the reference's, 1:1 (goldens extracted from
+    the reference's own signature / argparse calls).  Ours may only ADD keyword arguments at the end."""
+    import inspect
+    import json
+
+    from maua_stylegan2_b200 import generate_audiovisual as GA
+
+    ref_sig = json.loads(str(G["generate_signature"]))
+    ours = [[n, None if p.default is inspect.Parameter.empty else repr(p.default)]
+            for n, p in inspect.signature(GA.generate).parameters.items()]
+    for (rn, rd), (on, od) in zip(ref_sig, ours):
+        assert rn == on, (rn, on)
+        if rn != "audioreactive_file":          # ours defaults to the packaged device-path default hook file
+            assert rd == od, (rn, rd, od)
+    assert [n for n, _ in ours[len(ref_sig):]] == ["audio", "sink", "generator", "latent_selection"]
+
+    ref_flags = json.loads(str(G["cli_flags"]))
+    kinds = {"str": str, "int": int, "float": float}
+    got = {f"--{flag}": (kind, default) for flag, kind, default in GA.CLI_FLAGS}
+    assert list(got) == [f[0] for f in ref_flags]
+    for flag, kind, default, action in ref_flags:
+        okind, odefault = got[flag]
+        if action == "store_true":
+            assert okind is None and odefault is False
+        else:
+            assert okind is kinds[kind]
+            if flag != "--audioreactive_file":
+                assert odefault == default, flag
+    args = GA.build_parser().parse_args(["--ckpt", "g.pt", "--audio_file", "a.wav", "--shuffle_latents", "--fps", "24"])
+    assert args.ckpt == "g.pt" and args.shuffle_latents and args.fps == 24 and args.G_res == 1024
+
+
+def test_hook_discovery_and_override(tmp_path):
+    """Hooks are found by name in --audioreactive_file, missing ones reported and left None, OVERRIDE returned
+    (generate_audiovisual.py:262-292)."""
+    from maua_stylegan2_b200 import generate_audiovisual as GA
+
+    f = tmp_path / "hooks.py"
+    f.write_text("OVERRIDE = dict(fps=24, out_size=1920)\n"
+                 "def initialize(args):\n    args.flag = 1\n    return args\n"
+                 "def get_truncation(args):\n    return 0.7\n")
+    funcs, override = GA.load_hooks(str(f))
+    assert set(funcs) == set(GA.HOOKS)
+    assert funcs["initialize"] is not None and funcs["get_truncation"](None) == 0.7
+    assert funcs["get_latents"] is None and funcs["get_noise"] is None and funcs["get_bends"] is None
+    assert override == {"fps": 24, "out_size": 1920}
+    default_funcs, default_override = GA.load_hooks(GA.DEFAULT_HOOK_FILE)
+    assert all(default_funcs[k] is not None for k in ("initialize", "get_latents", "get_noise")) and default_override == {}
