@@ -165,7 +165,7 @@ def audio_glue_cases(ar):
     return out
 
 
-def plugin_cases(ar):
+def plugin_cases(ar, ref_sg2=None):
     """audioreactive/latent.py functions the example hook files call: perlin_noise
     (its `.cuda()` calls are made a no-op for this CPU run; the arithmetic is untouched), spline_loops, slerp."""
     out = {}
@@ -213,6 +213,21 @@ def plugin_cases(ar):
             kw = {k.arg: ast.literal_eval(k.value) if not isinstance(k.value, ast.Name) else k.value.id for k in node.keywords}
             flags.append([node.args[0].value, kw.get("type"), kw.get("default"), kw.get("action")])
     out["cli_flags"] = np.array(json.dumps(flags))
+    # model surface: Generator constructor / forward signatures and the state_dict layout real checkpoints carry
+    if ref_sg2 is not None:
+        def sig(fn):
+            return [[n, None if p.default is inspect.Parameter.empty else repr(p.default)]
+                    for n, p in inspect.signature(fn).parameters.items()]
+
+        out["generator_init_signature"] = np.array(json.dumps(sig(ref_sg2.Generator.__init__)))
+        out["generator_forward_signature"] = np.array(json.dumps(sig(ref_sg2.Generator.forward)))
+        for tag, kw in (("1024_cm2_const", dict(size=1024, channel_multiplier=2, constant_input=True)),
+                        ("512_cm1_noconst", dict(size=512, channel_multiplier=1, constant_input=False)),
+                        ("256_cm2_1920", dict(size=256, channel_multiplier=2, constant_input=True, output_size=1920))):
+            g = ref_sg2.Generator(kw.pop("size"), 512, 8, **kw)
+            out[f"state_dict_{tag}"] = np.array(json.dumps({k: list(v.shape) for k, v in g.state_dict().items()}))
+            out[f"layout_{tag}"] = np.array([g.n_latent, g.num_layers, g.log_size])
+            del g
     t = torch.arange(10)
     out["wrap_8_5"] = ar.wrapping_slice(t, 8, 5).numpy()
     out["wrap_2_4"] = ar.wrapping_slice(t, 2, 4).numpy()
@@ -222,7 +237,7 @@ def plugin_cases(ar):
 def main():
     op, ref_sg2, ar = import_reference()
     if "--plugins" in sys.argv:
-        np.savez_compressed(os.path.join(HERE, "plugins.npz"), **plugin_cases(ar))
+        np.savez_compressed(os.path.join(HERE, "plugins.npz"), **plugin_cases(ar, ref_sg2))
         return
     torch.set_grad_enabled(False)
     np.savez_compressed(os.path.join(HERE, "ops_golden.npz"), **ops_cases(op))

@@ -185,3 +185,32 @@ def test_hook_discovery_and_override(tmp_path):
     assert override == {"fps": 24, "out_size": 1920}
     default_funcs, default_override = GA.load_hooks(GA.DEFAULT_HOOK_FILE)
     assert all(default_funcs[k] is not None for k in ("initialize", "get_latents", "get_noise")) and default_override == {}
+
+
+def test_generator_surface_matches_reference():
+    """Generator constructor / forward parameters and the full state_dict layout (every key and shape, including the
+    noise buffers and FIR kernels) equal the reference's for config-f 1024, config-e 512 --noconst and a 1920-wide
+    output (goldens from the reference classes themselves)."""
+    import inspect
+    import json
+
+    from maua_stylegan2_b200.stylegan2 import Generator
+
+    def sig(fn):
+        return [[n, None if p.default is inspect.Parameter.empty else repr(p.default)]
+                for n, p in inspect.signature(fn).parameters.items()]
+
+    for key, fn, extra in (("generator_init_signature", Generator.__init__, ["impl", "precision"]),
+                           ("generator_forward_signature", Generator.forward, ["return_u8"])):
+        ref = json.loads(str(G[key]))
+        ours = sig(fn)
+        assert ours[:len(ref)] == ref, key
+        assert [n for n, _ in ours[len(ref):]] == extra
+    for tag, kw in (("1024_cm2_const", dict(size=1024, channel_multiplier=2, constant_input=True)),
+                    ("512_cm1_noconst", dict(size=512, channel_multiplier=1, constant_input=False)),
+                    ("256_cm2_1920", dict(size=256, channel_multiplier=2, constant_input=True, output_size=1920))):
+        ref = json.loads(str(G[f"state_dict_{tag}"]))
+        g = Generator(kw.pop("size"), 512, 8, **kw)
+        ours = {k: list(v.shape) for k, v in g.state_dict().items()}
+        assert ours == ref, (tag, set(ours) ^ set(ref))
+        assert [g.n_latent, g.num_layers, g.log_size] == list(G[f"layout_{tag}"])
