@@ -165,7 +165,7 @@ def audio_glue_cases(ar):
     return out
 
 
-def plugin_cases(ar, ref_sg2=None):
+def plugin_cases(ar, ref_sg2=None, ref_op=None):
     """audioreactive/latent.py functions the example hook files call: perlin_noise
     (its `.cuda()` calls are made a no-op for this CPU run; the arithmetic is untouched), spline_loops, slerp."""
     out = {}
@@ -228,6 +228,22 @@ def plugin_cases(ar, ref_sg2=None):
             out[f"state_dict_{tag}"] = np.array(json.dumps({k: list(v.shape) for k, v in g.state_dict().items()}))
             out[f"layout_{tag}"] = np.array([g.n_latent, g.num_layers, g.log_size])
             del g
+    # helper-package / op / render call signatures (names, order, defaults)
+    if ref_sg2 is not None:
+        import render as ref_render
+
+        api = {}
+        for name in ("onsets", "rms", "raw_chroma", "chroma", "normalize", "percentile", "percentile_clip", "compress",
+                     "expand", "gaussian_filter", "load_audio", "set_SMF", "chroma_weight_latents", "slerp", "slerp_loops",
+                     "spline_loops", "wrapping_slice", "generate_latents", "save_latents", "load_latents", "perlin_noise"):
+            api["ar." + name] = sig(getattr(ar, name))
+        for name in ("NetworkBend", "AddNoise", "Translate", "Zoom", "Rotate"):
+            api["ar." + name] = sig(getattr(ar, name).__init__)
+        api["op.upfirdn2d"] = sig(ref_op.upfirdn2d)
+        api["op.fused_leaky_relu"] = sig(ref_op.fused_leaky_relu)
+        api["op.FusedLeakyReLU"] = sig(ref_op.FusedLeakyReLU.__init__)
+        api["render.render"] = sig(ref_render.render)
+        out["api_signatures"] = np.array(json.dumps(api))
     t = torch.arange(10)
     out["wrap_8_5"] = ar.wrapping_slice(t, 8, 5).numpy()
     out["wrap_2_4"] = ar.wrapping_slice(t, 2, 4).numpy()
@@ -237,7 +253,7 @@ def plugin_cases(ar, ref_sg2=None):
 def main():
     op, ref_sg2, ar = import_reference()
     if "--plugins" in sys.argv:
-        np.savez_compressed(os.path.join(HERE, "plugins.npz"), **plugin_cases(ar, ref_sg2))
+        np.savez_compressed(os.path.join(HERE, "plugins.npz"), **plugin_cases(ar, ref_sg2, op))
         return
     torch.set_grad_enabled(False)
     np.savez_compressed(os.path.join(HERE, "ops_golden.npz"), **ops_cases(op))

@@ -214,3 +214,29 @@ def test_generator_surface_matches_reference():
         ours = {k: list(v.shape) for k, v in g.state_dict().items()}
         assert ours == ref, (tag, set(ours) ^ set(ref))
         assert [g.n_latent, g.num_layers, g.log_size] == list(G[f"layout_{tag}"])
+
+
+def test_helper_op_and_render_signatures_match_reference():
+    """Every public helper of `audioreactive`, the `op` functions and `render.render` take the reference's parameters
+    (names, order, defaults); ours may only append keyword arguments (`dtype`, `sink`)."""
+    import inspect
+    import json
+    import re
+
+    from maua_stylegan2_b200 import audioreactive as ar
+    from maua_stylegan2_b200 import op, render
+
+    def sig(fn):
+        return [[n, None if p.default is inspect.Parameter.empty else re.sub(r" at 0x[0-9a-f]+", "", repr(p.default))]
+                for n, p in inspect.signature(fn).parameters.items()]
+
+    api = json.loads(str(G["api_signatures"]))
+    assert len(api) == 30
+    allowed_extra = {"ar.perlin_noise": ["dtype"], "render.render": ["sink"]}
+    for key, ref in api.items():
+        ref = [[n, None if d is None else re.sub(r" at 0x[0-9a-f]+", "", d)] for n, d in ref]
+        mod, name = key.split(".")
+        obj = getattr({"ar": ar, "op": op, "render": render}[mod], name)
+        ours = sig(obj.__init__ if inspect.isclass(obj) else obj)
+        assert ours[:len(ref)] == ref, key
+        assert [n for n, _ in ours[len(ref):]] == allowed_extra.get(key, []), key
