@@ -48,7 +48,7 @@ def strided(t, n=6):
     return t[:, ::cs, ::s, ::s].contiguous().numpy()
 
 
-def gen_case(ref_sg2, size, cm, batch, seed, psi_lo):
+def gen_case(ref_sg2, size, cm, batch, seed, psi_lo, store_noise=True):
     from oracle import stylegan2_oracle as O
 
     sd = O.synth_state_dict(size, channel_multiplier=cm, seed=seed)
@@ -74,8 +74,9 @@ def gen_case(ref_sg2, size, cm, batch, seed, psi_lo):
                         return_activation_maps=True)
     out = {"size": size, "cm": cm, "seed": seed, "z": z.numpy(), "w": w.numpy(), "latent": latent.numpy(),
            "psi": psi.numpy(), "truncation_latent": tl.numpy(), "image": image.numpy(), "noise_none": np.array([2])}
+    out["batch"] = batch
     for l, n in enumerate(noise):
-        if n is not None:
+        if n is not None and store_noise:   # otherwise the test regenerates it: same PCG64 stream, same draw order
             out[f"noise_{l}"] = n.numpy()
     for l, a in enumerate(acts):
         out[f"act_{l}"] = strided(a)
@@ -252,6 +253,11 @@ def plugin_cases(ar, ref_sg2=None, ref_op=None):
 
 def main():
     op, ref_sg2, ar = import_reference()
+    if "--g256" in sys.argv:
+        torch.set_grad_enabled(False)
+        np.savez_compressed(os.path.join(HERE, "generator_g256.npz"),
+                            **gen_case(ref_sg2, 256, 2, 2, seed=7, psi_lo=0.5, store_noise=False))
+        return
     if "--plugins" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "plugins.npz"), **plugin_cases(ar, ref_sg2, op))
         return
@@ -259,6 +265,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ops_golden.npz"), **ops_cases(op))
     np.savez_compressed(os.path.join(HERE, "generator_g32.npz"), **gen_case(ref_sg2, 32, 2, 2, seed=3, psi_lo=0.5))
     np.savez_compressed(os.path.join(HERE, "generator_g128.npz"), **gen_case(ref_sg2, 128, 1, 1, seed=5, psi_lo=0.7))
+    np.savez_compressed(os.path.join(HERE, "generator_g256.npz"),   # BASELINE configs[0] architecture (256^2, cm=2)
+                        **gen_case(ref_sg2, 256, 2, 2, seed=7, psi_lo=0.5, store_noise=False))
     np.savez_compressed(os.path.join(HERE, "audio_glue.npz"), **audio_glue_cases(ar))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
