@@ -84,6 +84,62 @@ def gen_case(ref_sg2, size, cm, batch, seed, psi_lo, store_noise=True):
     return out
 
 
+class Affine(torch.nn.Module):
+    """x * a + b — a stand-in for a user bend (any nn.Module is allowed, README.md:120-146 of the reference)."""
+
+    def __init__(self, a, b):
+        super().__init__()
+        self.a, self.b = a, b
+
+    def forward(self, x):
+        return x * self.a + self.b
+
+
+class FlipW(torch.nn.Module):
+    def forward(self, x):
+        return torch.flip(x, dims=(3,))
+
+
+def bend_list():
+    """The bends of the `bends` fixture: widen the constant input 4x4 -> 4x8 (layer 0, as tauceti.py / kelp.py do),
+    rescale after the first up-conv (layer 2), mirror after the 16^2 conv (layer 5)."""
+    return [{"layer": 0, "transform": torch.nn.ReplicationPad2d((2, 2, 0, 0))},
+            {"layer": 2, "transform": Affine(0.5, 0.1)},
+            {"layer": 5, "transform": FlipW()}]
+
+
+def gen_bend_case(ref_sg2, size=32, cm=2, batch=2, seed=9):
+    """Reference Generator.forward with transform_dict_list (models/stylegan2.py:297-307,548-569): pins WHERE each layer id
+    is applied and the non-square (H x 2H) data flow.  Only outputs are stored; inputs are redrawn from the seed."""
+    from oracle import stylegan2_oracle as O
+
+    sd = O.synth_state_dict(size, channel_multiplier=cm, seed=seed)
+    g = ref_sg2.Generator(size, 512, 8, channel_multiplier=cm, constant_input=True, output_size=size)
+    g.load_state_dict(sd, strict=False)
+    g.eval()
+    latent, noise, tl = bend_case_inputs(size, batch, seed)
+    g.truncation_latent = tl
+    image, acts = g(latent, noise=list(noise), truncation=torch.ones(batch), input_is_latent=True, randomize_noise=False,
+                    return_activation_maps=True, transform_dict_list=bend_list())
+    out = {"size": size, "cm": cm, "seed": seed, "batch": batch, "image": image.numpy()}
+    for l, a in enumerate(acts):
+        out[f"act_{l}"] = strided(a)
+        out[f"act_{l}_absmax"] = np.array(a.abs().max().item(), np.float32)
+        out[f"act_{l}_shape"] = np.array(a.shape)
+    return out
+
+
+def bend_case_inputs(size, batch, seed):
+    from oracle import stylegan2_oracle as O
+
+    _, num_layers, n_latent = O.layout(size)
+    rng = np.random.Generator(np.random.PCG64(seed + 2000))
+    latent = torch.from_numpy(rng.standard_normal((batch, n_latent, 512)).astype(np.float32)) * 0.7
+    noise = [torch.from_numpy(rng.standard_normal((batch, 1, 2 ** ((l + 5) // 2), 2 * 2 ** ((l + 5) // 2))).astype(np.float32))
+             for l in range(num_layers)]
+    return latent, noise, torch.zeros(1, 512)
+
+
 def ops_cases(op):
     rng = np.random.Generator(np.random.PCG64(7))
     out = {}
@@ -253,6 +309,10 @@ def plugin_cases(ar, ref_sg2=None, ref_op=None):
 
 def main():
     op, ref_sg2, ar = import_reference()
+    if "--bends" in sys.argv:
+        torch.set_grad_enabled(False)
+        np.savez_compressed(os.path.join(HERE, "generator_bends.npz"), **gen_bend_case(ref_sg2))
+        return
     if "--g256" in sys.argv:
         torch.set_grad_enabled(False)
         np.savez_compressed(os.path.join(HERE, "generator_g256.npz"),
@@ -268,6 +328,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "generator_g256.npz"),   # BASELINE configs[0] architecture (256^2, cm=2)
                         **gen_case(ref_sg2, 256, 2, 2, seed=7, psi_lo=0.5, store_noise=False))
     np.savez_compressed(os.path.join(HERE, "audio_glue.npz"), **audio_glue_cases(ar))
+    np.savez_compressed(os.path.join(HERE, "generator_bends.npz"), **gen_bend_case(ref_sg2))
+    np.savez_compressed(os.path.join(HERE, "plugins.npz"), **plugin_cases(ar, ref_sg2, op))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -89,3 +89,22 @@ def test_generator_oracle_matches_reference(golden_dir, fname):
     for l, a in enumerate(acts):
         ref = g[f"act_{l}"]
         assert np.abs(strided(a) - ref).max() <= 2e-5 * float(g[f"act_{l}_absmax"]), l
+
+
+def test_generator_oracle_with_bends_matches_reference(golden_dir):
+    """transform_dict_list: layer-id placement (0 = constant input, 2 = first up-conv, 5 = 16^2 conv) and the non-square
+    H x 2H data flow, against the reference's own forward with the same bends (generator_bends.npz)."""
+    from tests.golden.make_golden import bend_case_inputs, bend_list, strided
+
+    g = _load(golden_dir, "generator_bends.npz")
+    size, cm, seed, batch = int(g["size"]), int(g["cm"]), int(g["seed"]), int(g["batch"])
+    sd = O.synth_state_dict(size, channel_multiplier=cm, seed=seed)
+    latent, noise, tl = bend_case_inputs(size, batch, seed)
+    with torch.no_grad():
+        image, acts = O.generator_forward(sd, size, latent, noise, torch.ones(batch), tl, channel_multiplier=cm,
+                                          bends=bend_list())
+    assert tuple(image.shape) == (batch, 3, size, 2 * size) == g["image"].shape
+    assert np.abs(image.numpy() - g["image"]).max() <= 2e-5 * np.abs(g["image"]).max()
+    for l, a in enumerate(acts):
+        assert list(a.shape) == list(g[f"act_{l}_shape"]), l
+        assert np.abs(strided(a) - g[f"act_{l}"]).max() <= 2e-5 * float(g[f"act_{l}_absmax"]), l
