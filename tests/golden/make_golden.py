@@ -219,6 +219,13 @@ def audio_glue_cases(ar):
     n = torch.from_numpy(rng.uniform(-1, 3, 77).astype(np.float32))
     out["norm_x"] = n.numpy()
     out["norm_y"] = ar.normalize(n.clone()).numpy()
+    # compress / expand / percentile (signal.py:257-316)
+    e = torch.from_numpy(rng.uniform(0, 1, 200).astype(np.float32))
+    out["dyn_x"] = e.numpy()
+    out["dyn_compress"] = ar.compress(e.clone(), 0.6, 0.25).numpy()
+    out["dyn_compress_inv"] = ar.compress(e.clone(), 0.3, 0.5, invert=True).numpy()
+    out["dyn_expand"] = ar.expand(e.clone(), 0.8, 10).numpy()
+    out["dyn_percentiles"] = np.array([ar.percentile(e, p) for p in (0, 10, 50, 97, 100)], np.float32)
     return out
 
 
@@ -309,6 +316,9 @@ def plugin_cases(ar, ref_sg2=None, ref_op=None):
 
 def main():
     op, ref_sg2, ar = import_reference()
+    if "--glue" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "audio_glue.npz"), **audio_glue_cases(ar))
+        return
     if "--bends" in sys.argv:
         torch.set_grad_enabled(False)
         np.savez_compressed(os.path.join(HERE, "generator_bends.npz"), **gen_bend_case(ref_sg2))

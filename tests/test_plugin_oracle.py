@@ -240,3 +240,18 @@ def test_helper_op_and_render_signatures_match_reference():
         ours = sig(obj.__init__ if inspect.isclass(obj) else obj)
         assert ours[:len(ref)] == ref, key
         assert [n for n, _ in ours[len(ref):]] == allowed_extra.get(key, []), key
+
+
+def test_dynamics_helpers_match_reference_on_host_tensors():
+    """normalize / compress / expand / percentile are plain tensor expressions in the product too (no kernel), so they
+    are checked HERE, on CPU tensors, against values the reference functions returned (audio_glue.npz)."""
+    from maua_stylegan2_b200.audioreactive import signal as S
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "audio_glue.npz"))
+    x = torch.from_numpy(g["dyn_x"])
+    np.testing.assert_allclose(S.compress(x.clone(), 0.6, 0.25).numpy(), g["dyn_compress"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(S.compress(x.clone(), 0.3, 0.5, invert=True).numpy(), g["dyn_compress_inv"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(S.expand(x.clone(), 0.8, 10).numpy(), g["dyn_expand"], rtol=1e-6, atol=1e-7)
+    got = np.array([S.percentile(x, p) for p in (0, 10, 50, 97, 100)], np.float32)
+    assert np.array_equal(got, g["dyn_percentiles"])
+    np.testing.assert_allclose(S.normalize(torch.from_numpy(g["norm_x"]).clone()).numpy(), g["norm_y"], rtol=1e-6, atol=1e-7)
