@@ -41,7 +41,8 @@ def make_kernel(k):
     return k / k.sum()
 
 
-def synth_state_dict(size, style_dim=512, n_mlp=8, channel_multiplier=2, seed=0, perturb=0.1, lr_mlp=0.01):
+def synth_state_dict(size, style_dim=512, n_mlp=8, channel_multiplier=2, seed=0, perturb=0.1, lr_mlp=0.01,
+                     noconst=False):
     """Deterministic random-init parameters with the reference's key layout and init
     distributions (`models/stylegan2.py:127,205,260,273,354`, `op/fused_act.py:78`), drawn from numpy's PCG64
     (stable across torch versions).  Zero-initialised parameters (noise.weight, activate.bias, to_rgb bias)
@@ -88,6 +89,12 @@ def synth_state_dict(size, style_dim=512, n_mlp=8, channel_multiplier=2, seed=0,
     for l in range(num_layers):
         res = (l + 5) // 2
         sd[f"noises.noise_{l}"] = randn(1, 1, 2 ** res, 2 ** res)
+    if noconst:  # LatentInput instead of ConstantInput (`models/stylegan2.py:281-288`); drawn last: other keys unchanged
+        n = ch[4] * 16
+        sd["input.input"] = randn(1)
+        sd["input.linear.weight"] = randn(n, style_dim)
+        sd["input.linear.bias"] = randn(n) * perturb
+        sd["input.activate.bias"] = randn(n) * perturb
     return sd
 
 
@@ -213,7 +220,14 @@ def generator_forward(sd, size, latent, noise, truncation, truncation_latent, ch
     latent = tl[None, ...] + truncation.to(dtype)[:, None, None] * (latent - tl[None, ...])
 
     acts = []
-    out = sd["input.input"].to(dtype).repeat(b, 1, 1, 1)
+    if "input.linear.weight" in sd:
+        # LatentInput.forward (`models/stylegan2.py:290-294`, --noconst): EqualLinear(fused_lrelu) of the (truncated) first
+        # latent row, then a second FusedLeakyReLU with its own bias, reshaped to [B, C, 4, 4]
+        out = equal_linear(latent[:, 0], sd["input.linear.weight"].to(dtype), sd["input.linear.bias"].to(dtype),
+                           activation=True)
+        out = fused_leaky_relu(out, sd["input.activate.bias"].to(dtype)).reshape(b, -1, 4, 4)
+    else:
+        out = sd["input.input"].to(dtype).repeat(b, 1, 1, 1)
     out = apply_bends(out, 0, bends)
     out = styled_conv(out, latent[:, 0], noise[0], sd, "conv1", False)
     out = apply_bends(out, 1, bends)

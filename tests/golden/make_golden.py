@@ -129,6 +129,39 @@ def gen_bend_case(ref_sg2, size=32, cm=2, batch=2, seed=9):
     return out
 
 
+def gen_noconst_case(ref_sg2, size=32, cm=2, batch=2, seed=13):
+    """Reference forward with LatentInput (`--noconst`, models/stylegan2.py:281-294); outputs only, inputs from the seed."""
+    from oracle import stylegan2_oracle as O
+
+    sd = O.synth_state_dict(size, channel_multiplier=cm, seed=seed, noconst=True)
+    g = ref_sg2.Generator(size, 512, 8, channel_multiplier=cm, constant_input=False, output_size=size)
+    missing, unexpected = g.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    g.eval()
+    latent, noise, tl, psi = noconst_case_inputs(size, batch, seed)
+    g.truncation_latent = tl
+    image, acts = g(latent, noise=list(noise), truncation=psi, input_is_latent=True, randomize_noise=False,
+                    return_activation_maps=True)
+    out = {"size": size, "cm": cm, "seed": seed, "batch": batch, "image": image.numpy()}
+    for l, a in enumerate(acts):
+        out[f"act_{l}"] = strided(a)
+        out[f"act_{l}_absmax"] = np.array(a.abs().max().item(), np.float32)
+    return out
+
+
+def noconst_case_inputs(size, batch, seed):
+    from oracle import stylegan2_oracle as O
+
+    _, num_layers, n_latent = O.layout(size)
+    rng = np.random.Generator(np.random.PCG64(seed + 3000))
+    latent = torch.from_numpy(rng.standard_normal((batch, n_latent, 512)).astype(np.float32)) * 0.7
+    noise = [torch.from_numpy(rng.standard_normal((batch, 1, 2 ** ((l + 5) // 2), 2 ** ((l + 5) // 2))).astype(np.float32))
+             for l in range(num_layers)]
+    tl = torch.from_numpy(rng.standard_normal((1, 512)).astype(np.float32)) * 0.1
+    psi = torch.from_numpy(rng.uniform(0.5, 1.0, batch).astype(np.float32))
+    return latent, noise, tl, psi
+
+
 def bend_case_inputs(size, batch, seed):
     from oracle import stylegan2_oracle as O
 
@@ -319,6 +352,10 @@ def main():
     if "--glue" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "audio_glue.npz"), **audio_glue_cases(ar))
         return
+    if "--noconst" in sys.argv:
+        torch.set_grad_enabled(False)
+        np.savez_compressed(os.path.join(HERE, "generator_noconst.npz"), **gen_noconst_case(ref_sg2))
+        return
     if "--bends" in sys.argv:
         torch.set_grad_enabled(False)
         np.savez_compressed(os.path.join(HERE, "generator_bends.npz"), **gen_bend_case(ref_sg2))
@@ -339,6 +376,7 @@ def main():
                         **gen_case(ref_sg2, 256, 2, 2, seed=7, psi_lo=0.5, store_noise=False))
     np.savez_compressed(os.path.join(HERE, "audio_glue.npz"), **audio_glue_cases(ar))
     np.savez_compressed(os.path.join(HERE, "generator_bends.npz"), **gen_bend_case(ref_sg2))
+    np.savez_compressed(os.path.join(HERE, "generator_noconst.npz"), **gen_noconst_case(ref_sg2))
     np.savez_compressed(os.path.join(HERE, "plugins.npz"), **plugin_cases(ar, ref_sg2, op))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -108,3 +108,20 @@ def test_generator_oracle_with_bends_matches_reference(golden_dir):
     for l, a in enumerate(acts):
         assert list(a.shape) == list(g[f"act_{l}_shape"]), l
         assert np.abs(strided(a) - g[f"act_{l}"]).max() <= 2e-5 * float(g[f"act_{l}_absmax"]), l
+
+
+def test_generator_oracle_noconst_matches_reference(golden_dir):
+    """`--noconst` (LatentInput, models/stylegan2.py:281-294): first latent row -> EqualLinear(fused_lrelu) ->
+    FusedLeakyReLU -> [B,512,4,4], with per-sample truncation, against the reference's forward."""
+    from tests.golden.make_golden import noconst_case_inputs, strided
+
+    g = _load(golden_dir, "generator_noconst.npz")
+    size, cm, seed, batch = int(g["size"]), int(g["cm"]), int(g["seed"]), int(g["batch"])
+    sd = O.synth_state_dict(size, channel_multiplier=cm, seed=seed, noconst=True)
+    assert sd["input.linear.weight"].shape == (8192, 512) and sd["input.input"].shape == (1,)
+    latent, noise, tl, psi = noconst_case_inputs(size, batch, seed)
+    with torch.no_grad():
+        image, acts = O.generator_forward(sd, size, latent, noise, psi, tl, channel_multiplier=cm)
+    assert np.abs(image.numpy() - g["image"]).max() <= 2e-5 * np.abs(g["image"]).max()
+    for l, a in enumerate(acts):
+        assert np.abs(strided(a) - g[f"act_{l}"]).max() <= 2e-5 * float(g[f"act_{l}_absmax"]), l

@@ -1,0 +1,88 @@
+"""GPU parity cases written AFTER this round's GPU budget was spent: they have not run on a B200 yet, so they are
+non-strict xfail (XPASS when green, never a suite failure) and sorted last.  Each compares the product path directly with
+fixtures produced by the UNMODIFIED reference (tests/golden/make_golden.py); the oracle is already green on all of them
+(tests/test_oracle_golden.py).  Round 2: run them, drop the marker."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import stylegan2_oracle as O
+from tests.util import GOLDEN, rel_err, strided
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: not yet run on a B200")]
+
+
+def _generator(size, cm, sd, impl, constant_input=True):
+    from maua_stylegan2_b200.stylegan2 import Generator
+
+    g = Generator(size, 512, 8, channel_multiplier=cm, constant_input=constant_input, output_size=size, impl=impl)
+    missing, unexpected = g.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    return g.cuda().eval()
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_noconst_generator_matches_reference_golden(impl):
+    """--noconst (LatentInput, models/stylegan2.py:281-294) with per-sample truncation."""
+    from tests.golden.make_golden import noconst_case_inputs
+
+    g = np.load(os.path.join(GOLDEN, "generator_noconst.npz"))
+    size, cm, seed, batch = int(g["size"]), int(g["cm"]), int(g["seed"]), int(g["batch"])
+    sd = O.synth_state_dict(size, channel_multiplier=cm, seed=seed, noconst=True)
+    gen = _generator(size, cm, sd, impl, constant_input=False)
+    latent, noise, tl, psi = noconst_case_inputs(size, batch, seed)
+    gen.truncation_latent = tl.cuda()
+    with torch.no_grad():
+        img, acts = gen(latent.cuda(), noise=[n.cuda() for n in noise], truncation=psi.cuda(), input_is_latent=True,
+                        randomize_noise=False, return_activation_maps=True)
+    tol = 2e-5 if impl == "simt" else 1e-3
+    assert rel_err(img.cpu().numpy(), g["image"]) < tol
+    for l, a in enumerate(acts):
+        assert np.abs(strided(a) - g[f"act_{l}"]).max() <= tol * float(g[f"act_{l}_absmax"]), l
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_g256_generator_matches_reference_golden(impl):
+    """BASELINE configs[0] architecture (256^2, cm=2) against the reference's own CPU output."""
+    from tests.test_oracle_golden import regenerate_noise
+
+    g = np.load(os.path.join(GOLDEN, "generator_g256.npz"))
+    size, cm, seed = int(g["size"]), int(g["cm"]), int(g["seed"])
+    sd = O.synth_state_dict(size, channel_multiplier=cm, seed=seed)
+    gen = _generator(size, cm, sd, impl)
+    noise = regenerate_noise(g, size, seed)
+    gen.truncation_latent = torch.from_numpy(g["truncation_latent"]).cuda()
+    with torch.no_grad():
+        img, acts = gen(torch.from_numpy(g["latent"]).cuda(), noise=[n.cuda() if n is not None else None for n in noise],
+                        truncation=torch.from_numpy(g["psi"]).cuda(), input_is_latent=True, randomize_noise=False,
+                        return_activation_maps=True)
+    # (the noise=None layer uses the `noises.noise_2` buffer, which both sides load from the synthetic state dict)
+    tol = 2e-5 if impl == "simt" else 1e-3
+    assert rel_err(img.cpu().numpy(), g["image"]) < tol
+    for l, a in enumerate(acts):
+        assert np.abs(strided(a) - g[f"act_{l}"]).max() <= tol * float(g[f"act_{l}_absmax"]), l
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_bends_generator_matches_reference_golden(impl):
+    """transform_dict_list at layers 0 / 2 / 5 (widen to H x 2H, rescale, mirror) against the reference's forward."""
+    from tests.golden.make_golden import bend_case_inputs, bend_list
+
+    g = np.load(os.path.join(GOLDEN, "generator_bends.npz"))
+    size, cm, seed, batch = int(g["size"]), int(g["cm"]), int(g["seed"]), int(g["batch"])
+    sd = O.synth_state_dict(size, channel_multiplier=cm, seed=seed)
+    gen = _generator(size, cm, sd, impl)
+    latent, noise, tl = bend_case_inputs(size, batch, seed)
+    gen.truncation_latent = tl.cuda()
+    with torch.no_grad():
+        img, acts = gen(latent.cuda(), noise=[n.cuda() for n in noise], truncation=torch.ones(batch).cuda(),
+                        input_is_latent=True, randomize_noise=False, return_activation_maps=True,
+                        transform_dict_list=bend_list())
+    tol = 2e-5 if impl == "simt" else 1e-3
+    assert tuple(img.shape) == g["image"].shape
+    assert rel_err(img.cpu().numpy(), g["image"]) < tol
+    for l, a in enumerate(acts):
+        assert np.abs(strided(a) - g[f"act_{l}"]).max() <= tol * float(g[f"act_{l}_absmax"]), l
