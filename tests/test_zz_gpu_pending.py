@@ -86,3 +86,39 @@ def test_bends_generator_matches_reference_golden(impl):
     assert rel_err(img.cpu().numpy(), g["image"]) < tol
     for l, a in enumerate(acts):
         assert np.abs(strided(a) - g[f"act_{l}"]).max() <= tol * float(g[f"act_{l}_absmax"]), l
+
+
+def test_rewrites_hook_reweights_parameters_per_batch():
+    """get_rewrites contract (README.md:136-146 / render.py:126-131,160-167 of the reference): per batch, the parameter is
+    replaced by transform(original) with transform built from that batch's modulation slice.  Checked against direct
+    forwards of a generator whose weight was scaled by hand."""
+    from maua_stylegan2_b200.render import FramePipeline
+    from tests.util import make_generator
+
+    size, cm, batch = 32, 2, 4
+    g, sd = make_generator(size, cm, seed=21, impl="tc")
+    g.truncation_latent = torch.zeros(1, 512, device="cuda")
+    _, num_layers, n_latent = O.layout(size)
+    rng = np.random.Generator(np.random.PCG64(22))
+    latents = torch.from_numpy(rng.standard_normal((8, n_latent, 512)).astype(np.float32)) * 0.6
+    noise = [torch.from_numpy(rng.standard_normal((8, 1, 2 ** ((l + 5) // 2), 2 ** ((l + 5) // 2))).astype(np.float32))
+             for l in range(num_layers)]
+    name = "convs.1.conv.weight"
+    modulation = torch.tensor([0.5] * 4 + [2.0] * 4)
+    rewrites = {name: [lambda m: (lambda w: w * float(m.mean())), modulation]}
+    frames = []
+    pipe = FramePipeline(g, latents, noise, batch, truncation=1.0, rewrites=rewrites)
+    with torch.no_grad():
+        pipe.warmup()
+        pipe.run(lambda f: frames.append(f.copy()))
+    got = np.concatenate(frames)
+    assert got.shape == (8, size, size, 3)
+    for i, scale in enumerate((0.5, 2.0)):
+        ref_g, _ = make_generator(size, cm, seed=21, impl="tc")
+        ref_g.truncation_latent = torch.zeros(1, 512, device="cuda")
+        with torch.no_grad():
+            ref_g.convs[1].conv.weight.mul_(scale)
+            sl = slice(i * batch, (i + 1) * batch)
+            want, _ = ref_g(latents[sl].cuda(), noise=[n[sl].cuda() for n in noise], truncation=1.0, input_is_latent=True,
+                            randomize_noise=False, return_u8=True)
+        assert np.array_equal(got[sl], want.cpu().numpy()), i
