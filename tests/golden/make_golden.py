@@ -312,8 +312,10 @@ def plugin_cases(ar, ref_sg2=None, ref_op=None):
     out["cli_flags"] = np.array(json.dumps(flags))
     # model surface: Generator constructor / forward signatures and the state_dict layout real checkpoints carry
     if ref_sg2 is not None:
-        def sig(fn):
-            return [[n, None if p.default is inspect.Parameter.empty else repr(p.default)]
+        def sig(fn):  # defaults as repr, function addresses stripped (deterministic fixture)
+            import re
+
+            return [[n, None if p.default is inspect.Parameter.empty else re.sub(r" at 0x[0-9a-f]+", "", repr(p.default))]
                     for n, p in inspect.signature(fn).parameters.items()]
 
         out["generator_init_signature"] = np.array(json.dumps(sig(ref_sg2.Generator.__init__)))
