@@ -51,6 +51,10 @@ int maua_abi_version(void);
 const char* maua_last_error(void);
 /* Number of kernels launched through this library by the calling process (bench.py's gpu_launches). */
 long long maua_launch_count(void);
+/* Kernel variant and tile configuration chosen by the calling thread's last maua_modconv_tc call, e.g.
+ * "v2 up=0 R=4 BN=32 cat=1 groups=1 AS=2 SA=2 SB=9 grid=148" or "v1 up=1 KC=64 BN=128 S=4 grid=96"
+ * (diagnostics / tests: which of the two tensor-core kernels a shape was routed to). */
+const char* maua_modconv_tc_last_config(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Operator ABI (reference op/ extensions)

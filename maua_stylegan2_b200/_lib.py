@@ -73,6 +73,7 @@ _SPECIAL = {
     "maua_abi_version": (C.c_int, []),
     "maua_last_error": (C.c_char_p, []),
     "maua_launch_count": (C.c_longlong, []),
+    "maua_modconv_tc_last_config": (C.c_char_p, []),
 }
 
 _lib = None
@@ -113,6 +114,11 @@ def stream_ptr(device=None):
 
 def launch_count():
     return int(lib().maua_launch_count())
+
+
+def last_conv_config():
+    """Variant / tile configuration of this thread's last maua_modconv_tc call (diagnostics, tests)."""
+    return lib().maua_modconv_tc_last_config().decode()
 
 
 # Optional per-launch timing (bench.py's roofline pass): PROFILE = {"names": set, "events": []}; TAG is attached to

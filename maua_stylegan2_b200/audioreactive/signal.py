@@ -282,27 +282,47 @@ def gaussian_filter(x, sigma, causal=None):
     return y
 
 
+LOAD_SR = 22050  # librosa.load's default target rate: every frame constant below (N_FFT, HOP, HPSS widths) assumes it
+
+
 def load_audio(audio_file, offset=0, duration=-1, cache=True):
-    """signal.py:371-405 without librosa: .npy (float array + sibling .sr.txt or 22050 Hz) and PCM .wav are supported."""
+    """signal.py:371-405 without librosa: .npy (float array + sibling .sr.txt or 22050 Hz) and PCM / float .wav.
+
+    Like `rosa.load(audio_file, offset=offset, duration=duration)` the result is MONO at 22050 Hz: other sample rates
+    are converted with a polyphase resampler (scipy.signal.resample_poly; librosa uses soxr/resampy — same band limit,
+    different filter, hence "like").  Integer PCM is scaled by 2**(bits-1) (unsigned 8-bit recentred first)."""
     p = Path(audio_file)
     if p.suffix == ".npy":
         audio = np.load(p).astype(np.float32)
         sr_file = p.with_suffix(".sr.txt")
-        sr = int(sr_file.read_text()) if sr_file.exists() else 22050
+        sr = int(sr_file.read_text()) if sr_file.exists() else LOAD_SR
     elif p.suffix == ".wav":
         from scipy.io import wavfile
 
         sr, data = wavfile.read(p)
-        if data.dtype.kind == "i":
-            data = data.astype(np.float32) / np.iinfo(data.dtype).max
+        if data.dtype.kind == "u":      # 8-bit PCM is unsigned, centred on 128
+            bits = data.dtype.itemsize * 8
+            data = (data.astype(np.float32) - 2.0 ** (bits - 1)) / 2.0 ** (bits - 1)
+        elif data.dtype.kind == "i":
+            data = data.astype(np.float32) / 2.0 ** (data.dtype.itemsize * 8 - 1)
         audio = data.astype(np.float32)
-        if audio.ndim > 1:
-            audio = audio.mean(1)
     else:
         raise L.MauaError(f"cannot decode {p.suffix} without librosa/ffmpeg: convert to .wav or .npy")
-    start = int(offset * sr)
+    if audio.ndim > 1:
+        audio = audio.mean(1)
+    start = int(round(offset * sr))
     total = len(audio) / sr
-    if duration == -1 or total < duration:
-        duration = total - (offset if offset != 0 else 0)
-    audio = audio[start:start + int(duration * sr)]
+    if duration == -1 or total < duration:   # signal.py:386-389
+        duration = total
+        if offset != 0:
+            duration -= offset
+    audio = audio[start:start + int(round(duration * sr))]
+    if sr != LOAD_SR:
+        from math import gcd
+
+        from scipy.signal import resample_poly
+
+        g = gcd(int(sr), LOAD_SR)
+        audio = resample_poly(audio.astype(np.float64), LOAD_SR // g, int(sr) // g).astype(np.float32)
+        sr = LOAD_SR
     return audio, sr, duration

@@ -301,13 +301,10 @@ extern "C" int maua_blur_act_nhwc(const float* u, const float* k4, const MauaCon
     MAUA_CHECK_ARG(n_tiles < (1LL << 31), "blur_act_nhwc: too many tiles");
     const size_t smem = 2 * (size_t)BIN * BIN * BCH * 4 + 16 + 128;
     static const int rpt = [] { const char* e = getenv("MAUA_BLUR_RPT"); return e ? atoi(e) : 8; }();
-    static bool attr_done = false;
-    if (!attr_done) {
-      MAUA_CHECK_CUDA(cudaFuncSetAttribute(blur_act_nhwc_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      MAUA_CHECK_CUDA(cudaFuncSetAttribute(blur_act_nhwc_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_done = true;
-    }
-    const int grid = (int)(n_tiles < 148 * 2 ? n_tiles : 148 * 2);
+    MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(blur_act_nhwc_tma_kernel<8>), smem));
+    MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(blur_act_nhwc_tma_kernel<4>), smem));
+    const int n_sm = device_sm_count();
+    const int grid = (int)(n_tiles < n_sm * 2 ? n_tiles : n_sm * 2);
     if (rpt == 8)
       blur_act_nhwc_tma_kernel<8><<<grid, 256, smem, as_stream(stream)>>>(tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles);
     else

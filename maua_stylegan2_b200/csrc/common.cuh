@@ -12,8 +12,15 @@ namespace maua {
 // thread-local error text + process-wide launch counter (defined in common.cu)
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void set_conv_config(const char* fmt, ...);  // what maua_modconv_tc_last_config() reports (thread-local)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Per-DEVICE caches (defined in common.cu).  cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device/context
+// attribute and the SM count drives the tile policies: a process that renders on cuda:0 and then on cuda:1 must set /
+// query them again on the second device (a process-wide `static bool done` silently broke every >48 KB launch there).
+int device_sm_count();                                   // SMs of the CURRENT device (148 on B200)
+cudaError_t ensure_dyn_smem(const void* kernel, size_t bytes);  // raise the kernel's dynamic-smem limit to >= bytes
 
 #define MAUA_CHECK_ARG(cond, ...)            \
   do {                                       \

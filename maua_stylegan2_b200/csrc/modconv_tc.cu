@@ -429,12 +429,7 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
   // (BN, S): modelled cycles = waves * (per-CTA MMA time + fixed prologue/epilogue).  A wide N keeps the MMA efficient
   // (every 128 x N x 16 MMA fetches 4 KB of A whatever N is); when that leaves SMs idle the K loop is split over S
   // CTAs per tile (deterministic reduction through ep.workspace) instead of shrinking N.
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-  }
+  const int n_sm = device_sm_count();
   static const int force_s = [] { const char* e = getenv("MAUA_TC_SPLITK"); return e ? atoi(e) : 0; }();
   int bn = 16, best_s = 1;
   double best_cost = 1e30;
@@ -475,6 +470,8 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
     fprintf(stderr, "[modconv_tc v1] %s B%d %d->%d @%dx%d: tile %dx%dx%d (%d rows) m_tiles=%lld BN=%d S=%d stages=%d grid=%lld\n",
             up ? "up" : "same", batch, cin, cout, h, w, p.TB, p.TH, p.TW, p.rows, m_tiles, bn, p.S, stages,
             m_tiles * p.n_tiles * p.S);
+  set_conv_config("v1 up=%d KC=%d tile=%dx%dx%d BN=%d S=%d stages=%d grid=%lld", up, kc, p.TB, p.TH, p.TW, bn, p.S, stages,
+                  m_tiles * p.n_tiles * p.S);
   const size_t smem = (size_t)stages * (a_stage + b_stage) + 8 * (2 * p.SA + 2 * p.SB + 2) + 1024;
   MAUA_CHECK_ARG(smem <= 227 * 1024, "modconv_tc: shared memory budget exceeded");
   MAUA_CHECK_ARG(m_tiles * p.n_tiles * p.S < (1LL << 31), "modconv_tc: grid too large");
@@ -502,11 +499,7 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
   const unsigned grid = (unsigned)(m_tiles * p.n_tiles * p.S);
 #define MAUA_TC_LAUNCH(KCV, UPV)                                                                                   \
   do {                                                                                                             \
-    static size_t smem_set = 0; /* per instantiation; never called again during CUDA-graph capture */            \
-    if (smem > smem_set) {                                                                                         \
-      MAUA_CHECK_CUDA(cudaFuncSetAttribute(modconv_tc_kernel<KCV, UPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-      smem_set = smem;                                                                                             \
-    }                                                                                                              \
+    MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(modconv_tc_kernel<KCV, UPV>), smem));             \
     modconv_tc_kernel<KCV, UPV><<<grid, 192, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep);                       \
   } while (0)
   if (kc == 64) {

@@ -491,11 +491,17 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
                        cudaStream_t st) {
   using namespace tc2;
   const int GH = up ? h + 1 : h, GW = up ? w + 1 : w;
+  // MAUA_TC_FORCE="R,BN,cat,groups" (read on every call: tools/tune_tc2.py and the unit tests sweep it) pins the
+  // configuration and bypasses the size gate below; an infeasible forced configuration is an error, never a fallback.
+  int f_r = 0, f_bn = 0, f_cat = 0, f_groups = 0;
+  if (const char* f = getenv("MAUA_TC_FORCE")) {
+    if (sscanf(f, "%d,%d,%d,%d", &f_r, &f_bn, &f_cat, &f_groups) != 4) f_r = 0;
+  }
   // <= 32^2 (measured): v1's batch-folded tiles are faster — except the same-resolution Cout >= 256 layer at 32^2 once
   // the batch fills the machine with (R=1, BN=256) items (512->512 @32^2, batch 8: 0.088 ms vs 0.103 ms for v1).
   // MAUA_TC2_MIN_TILES overrides the threshold (experiments).
   static const int min_tiles = [] { const char* e = getenv("MAUA_TC2_MIN_TILES"); return e ? atoi(e) : 4; }();
-  if (GH < min_tiles * TH || GW < min_tiles * TW) {
+  if (!f_r && (GH < min_tiles * TH || GW < min_tiles * TW)) {
     const bool wide32 = !up && GH >= 2 * TH && GW >= 2 * TW && cout >= 256 && cout % 256 == 0 &&
                         (long long)ceil_div(GW, TW) * ceil_div(GH, TH) * batch * (cout / 256) >= 120;
     if (!wide32) return MAUA_E_UNSUPPORTED;
@@ -522,13 +528,6 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   // The search below (cost model) only decides when the preferred configuration is infeasible or leaves most SMs idle.
   int best_r = 0, best_bn = 0, best_cat = 0, best_groups = 1;
   static const int force_groups = [] { const char* e = getenv("MAUA_TC_GROUPS"); return e ? atoi(e) : 0; }();
-  // tools/tune_tc2.py: MAUA_TC_TUNE=1 makes every call read MAUA_TC_FORCE="R,BN,cat,groups"
-  static const bool tune = [] { const char* e = getenv("MAUA_TC_TUNE"); return e && e[0] == '1'; }();
-  int f_r = 0, f_bn = 0, f_cat = 0, f_groups = 0;
-  if (tune) {
-    const char* f = getenv("MAUA_TC_FORCE");
-    if (f && sscanf(f, "%d,%d,%d,%d", &f_r, &f_bn, &f_cat, &f_groups) != 4) f_r = 0;
-  }
   auto n_ctas = [&](int r, int bn, int groups) {
     return tiles_x * ceil_div(rows16, (long long)r) * batch * (cout / bn) * groups;
   };
@@ -629,18 +628,15 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   cols = 32;
   while (cols < p.AS * blk_cols * R * p.n_phase) cols <<= 1;
   p.tmem_cols = (uint32_t)cols;
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-  }
+  const int n_sm = device_sm_count();
   const long long grid = items < n_sm ? items : n_sm;
   static const bool debug = [] { const char* e = getenv("MAUA_TC_DEBUG"); return e && e[0] == '1'; }();
   if (debug)
     fprintf(stderr, "[modconv_tc2] %s B%d %d->%d @%dx%d: R=%d BN=%d cat=%d groups=%d resB=%d AS=%d SA=%d SB=%d smem=%zuKB tmem=%u items=%lld grid=%lld\n",
             up ? "up" : "same", batch, cin, cout, h, w, R, bn, p.cat, p.n_groups, p.resident_b, p.AS, p.SA, p.SB, smem / 1024, p.tmem_cols, items, grid);
 
+  set_conv_config("v2 up=%d R=%d BN=%d cat=%d groups=%d resB=%d AS=%d SA=%d SB=%d items=%lld grid=%lld", up, R, bn, p.cat,
+                  p.n_groups, p.resident_b, p.AS, p.SA, p.SB, items, grid);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   const auto swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const cuuint64_t adims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
@@ -661,11 +657,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   }
 #define MAUA_TC2_LAUNCH(KCV, UPV, MODEV)                                                                            \
   do {                                                                                                              \
-    static size_t smem_set = 0; /* per instantiation; never called again during CUDA-graph capture */            \
-    if (smem > smem_set) {                                                                                         \
-      MAUA_CHECK_CUDA(cudaFuncSetAttribute(modconv_tc2_kernel<KCV, UPV, MODEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-      smem_set = smem;                                                                                             \
-    }                                                                                                              \
+    MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(modconv_tc2_kernel<KCV, UPV, MODEV>), smem));    \
     modconv_tc2_kernel<KCV, UPV, MODEV><<<(unsigned)grid, THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep);      \
   } while (0)
   const int mode = n_products == 1 ? 0 : (p.cat ? 2 : 1);

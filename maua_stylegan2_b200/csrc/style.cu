@@ -185,12 +185,8 @@ extern "C" int maua_style_prologue_f32(const MauaStyleJob* jobs, int n_jobs, con
   cudaStream_t st = as_stream(stream);
   const size_t smem_s = (size_t)SB * style_dim * sizeof(float);
   const size_t smem_d = (size_t)SB * max_dim * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    MAUA_CHECK_CUDA(cudaFuncSetAttribute(style_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    MAUA_CHECK_CUDA(cudaFuncSetAttribute(style_d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_done = true;
-  }
+  MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(style_s_kernel), 64 * 1024));
+  MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(style_d_kernel), 64 * 1024));
   style_s_kernel<<<dim3(n_jobs, max_dim / SROWS, zb), 256, smem_s, st>>>(jobs, latent, mean, psi, psi_scalar,
                                                                         latent_trunc_out, batch, n_latent, style_dim);
   MAUA_CHECK_LAUNCH("style_prologue(s)");

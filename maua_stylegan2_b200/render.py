@@ -172,13 +172,25 @@ class FramePipeline:
                 item["truncation"] = self.truncation[sl].to(self.device, non_blocking=True)
                 self.h2d_bytes += item["truncation"].numel() * 4
             item["bends"] = []
+            staged = [item["latent"]] + [t for t in item["noise"] if t is not None]
+            if torch.is_tensor(item["truncation"]):
+                staged.append(item["truncation"])
             for bend in self.bends:
                 if "modulation" in bend:
                     mod = bend["modulation"][sl].to(self.device, non_blocking=True)
                     self.h2d_bytes += mod.numel() * 4
-                    item["bends"].append({"layer": bend["layer"], "transform": bend["transform"](mod)})
+                    staged.append(mod)
+                    transform = bend["transform"](mod)
+                    # tensors the transform factory derived from the modulation on the copy stream (module parameters /
+                    # buffers / attributes) are read by the compute stream as well
+                    if isinstance(transform, torch.nn.Module):
+                        staged += [t for t in list(transform.parameters()) + list(transform.buffers()) if t.is_cuda]
+                        for m in transform.modules():
+                            staged += [v for v in vars(m).values() if torch.is_tensor(v) and v.is_cuda]
+                    item["bends"].append({"layer": bend["layer"], "transform": transform})
                 else:
                     item["bends"].append({"layer": bend["layer"], "transform": bend["transform"]})
+            item["staged"] = staged
             item["ready"] = torch.cuda.Event()
             item["ready"].record(self.copy_stream)
         return item
@@ -200,7 +212,13 @@ class FramePipeline:
             setattr(mod, parts[-1], torch.nn.Parameter(new, requires_grad=False))
 
     def _render(self, item, n):
-        torch.cuda.current_stream(self.device).wait_event(item["ready"])
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(item["ready"])
+        # The staged tensors were allocated on the COPY stream: tell the caching allocator that the compute stream reads
+        # them, otherwise dropping `item` hands their blocks straight back to the copy stream's pool and the H2D of
+        # batch i+2 overwrites noise maps that batch i's forward (still running) has not read yet.
+        for t in item["staged"]:
+            t.record_stream(cur)
         self._apply_rewrites(n)
         frames, _ = self.g(styles=item["latent"], noise=item["noise"], truncation=item["truncation"],
                            transform_dict_list=item["bends"], randomize_noise=self.randomize_noise,

@@ -459,6 +459,12 @@ class Generator(nn.Module):
                     key.append((p.data_ptr(), p._version))
         return tuple(key)
 
+    def invalidate_plan(self):
+        """Drop the cached weight-derived plan (packed tensor-core weights, Wsq, style job tables).  The cache key follows
+        `(data_ptr, _version)` of every conv / modulation parameter, which in-place ops and `nn.Parameter` replacement
+        (render's `rewrites`) bump — edits made through `param.data` (`w.data.mul_()`) do NOT: call this after them."""
+        self._plan = None
+
     def _get_plan(self):
         key = self._plan_key()
         if self._plan is None or self._plan["key"] != key:

@@ -61,9 +61,22 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
                 raise L.MauaError(f"truncation has {psi_t.numel()} entries for a batch of {batch}")
         else:
             psi_s = float(truncation)
-        latent_t = torch.empty_like(latent)
-        L.call("maua_style_prologue_f32", bc["table"].data_ptr(), plan["n_jobs"], latent.data_ptr(), mean.data_ptr(),
-               L.ptr(psi_t), psi_s, latent_t.data_ptr(), batch, g.n_latent, g.style_dim, stream)
+        if latent.shape[1] < g.n_latent or latent.shape[2] != g.style_dim:
+            raise L.MauaError(f"latents of shape {tuple(latent.shape)}: need at least {g.n_latent} rows of {g.style_dim}")
+        if mean.numel() != g.style_dim:
+            # a per-layer mean latent ([n_latent, D], broadcast by the reference's `truncation_latent[None, ...]`,
+            # models/stylegan2.py:541-543): the lerp is evaluated here with the reference's own expression and the
+            # prologue kernel runs without truncation
+            psi_b = psi_t[:, None, None] if psi_t is not None else psi_s
+            latent = (mean[None, ...] + psi_b * (latent - mean[None, ...])).contiguous()
+            latent_t = latent
+            L.call("maua_style_prologue_f32", bc["table"].data_ptr(), plan["n_jobs"], latent.data_ptr(), None, None, 1.0,
+                   None, batch, latent.shape[1], g.style_dim, stream)
+        else:
+            # (rows beyond n_latent feed no layer: the kernel never writes them, so they are carried over untruncated)
+            latent_t = torch.empty_like(latent) if latent.shape[1] == g.n_latent else latent.clone()
+            L.call("maua_style_prologue_f32", bc["table"].data_ptr(), plan["n_jobs"], latent.data_ptr(), mean.data_ptr(),
+                   L.ptr(psi_t), psi_s, latent_t.data_ptr(), batch, latent.shape[1], g.style_dim, stream)
 
         # ---- input (models/stylegan2.py:547-548) --------------------------------------------------------------------
         from .stylegan2 import ConstantInput

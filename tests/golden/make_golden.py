@@ -48,7 +48,9 @@ def strided(t, n=6):
     return t[:, ::cs, ::s, ::s].contiguous().numpy()
 
 
-def gen_case(ref_sg2, size, cm, batch, seed, psi_lo, store_noise=True):
+def gen_case(ref_sg2, size, cm, batch, seed, psi_lo, store_noise=True, noise_none=(2,), image_stride=1):
+    """image_stride > 1 (1024^2 fixture): the image is stored as every image_stride-th pixel plus a full-resolution
+    128x128 centre crop (`image_crop`), so that the fixture stays small."""
     from oracle import stylegan2_oracle as O
 
     sd = O.synth_state_dict(size, channel_multiplier=cm, seed=seed)
@@ -66,14 +68,22 @@ def gen_case(ref_sg2, size, cm, batch, seed, psi_lo, store_noise=True):
         latent = latent + 0.05 * torch.from_numpy(rng.standard_normal(latent.shape).astype(np.float32))  # W+
         noise = [torch.from_numpy(rng.standard_normal((batch, 1, 2 ** ((l + 5) // 2), 2 ** ((l + 5) // 2))).astype(np.float32))
                  for l in range(num_layers)]
-        noise[2] = None  # exercise the buffer path (randomize_noise=False)
+        for l in noise_none:  # exercise the buffer path (randomize_noise=False)
+            noise[l] = None
         psi = torch.from_numpy(rng.uniform(psi_lo, 1.0, batch).astype(np.float32))
         tl = w.mean(0, keepdim=True) * 0.5
         g.truncation_latent = tl
         image, acts = g(latent, noise=list(noise), truncation=psi, input_is_latent=True, randomize_noise=False,
                         return_activation_maps=True)
     out = {"size": size, "cm": cm, "seed": seed, "z": z.numpy(), "w": w.numpy(), "latent": latent.numpy(),
-           "psi": psi.numpy(), "truncation_latent": tl.numpy(), "image": image.numpy(), "noise_none": np.array([2])}
+           "psi": psi.numpy(), "truncation_latent": tl.numpy(), "image": image.numpy(),
+           "noise_none": np.array(list(noise_none))}
+    if image_stride > 1:
+        c0 = size // 2 - 64
+        out["image"] = image[:, :, ::image_stride, ::image_stride].contiguous().numpy()
+        out["image_crop"] = image[:, :, c0:c0 + 128, c0:c0 + 128].contiguous().numpy()
+        out["image_stride"] = np.array(image_stride)
+        out["image_absmax"] = np.array(image.abs().max().item(), np.float32)
     out["batch"] = batch
     for l, n in enumerate(noise):
         if n is not None and store_noise:   # otherwise the test regenerates it: same PCG64 stream, same draw order
@@ -82,6 +92,16 @@ def gen_case(ref_sg2, size, cm, batch, seed, psi_lo, store_noise=True):
         out[f"act_{l}"] = strided(a)
         out[f"act_{l}_absmax"] = np.array(a.abs().max().item(), np.float32)
     return out
+
+
+def gen_case_1024(ref_sg2):
+    """BASELINE configs[1] architecture (1024^2 config-f, cm=2), ONE frame through the unmodified reference on CPU; like the
+    default hooks, noise maps wider than 256 are None (the generator's registered buffers are used, examples/default.py:29-30)."""
+    from oracle import stylegan2_oracle as O
+
+    _, num_layers, _ = O.layout(1024)
+    none = tuple(l for l in range(num_layers) if 2 ** ((l + 5) // 2) > 256)
+    return gen_case(ref_sg2, 1024, 2, 1, seed=11, psi_lo=0.7, store_noise=False, noise_none=none, image_stride=4)
 
 
 class Affine(torch.nn.Module):
@@ -367,6 +387,10 @@ def main():
         np.savez_compressed(os.path.join(HERE, "generator_g256.npz"),
                             **gen_case(ref_sg2, 256, 2, 2, seed=7, psi_lo=0.5, store_noise=False))
         return
+    if "--g1024" in sys.argv:
+        torch.set_grad_enabled(False)
+        np.savez_compressed(os.path.join(HERE, "generator_g1024.npz"), **gen_case_1024(ref_sg2))
+        return
     if "--plugins" in sys.argv:
         np.savez_compressed(os.path.join(HERE, "plugins.npz"), **plugin_cases(ar, ref_sg2, op))
         return
@@ -376,6 +400,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "generator_g128.npz"), **gen_case(ref_sg2, 128, 1, 1, seed=5, psi_lo=0.7))
     np.savez_compressed(os.path.join(HERE, "generator_g256.npz"),   # BASELINE configs[0] architecture (256^2, cm=2)
                         **gen_case(ref_sg2, 256, 2, 2, seed=7, psi_lo=0.5, store_noise=False))
+    np.savez_compressed(os.path.join(HERE, "generator_g1024.npz"), **gen_case_1024(ref_sg2))   # BASELINE configs[1]
     np.savez_compressed(os.path.join(HERE, "audio_glue.npz"), **audio_glue_cases(ar))
     np.savez_compressed(os.path.join(HERE, "generator_bends.npz"), **gen_bend_case(ref_sg2))
     np.savez_compressed(os.path.join(HERE, "generator_noconst.npz"), **gen_noconst_case(ref_sg2))

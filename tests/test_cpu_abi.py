@@ -45,16 +45,40 @@ def test_struct_layouts_match_c():
     assert ctypes.sizeof(L.ConvEpilogue) == 128
 
 
-def test_cpu_tensors_fail_loudly():
+def test_cpu_tensor_branch_matches_reference_goldens():
+    """The reference dispatches on `input.device.type` and CPU inputs keep working (op/upfirdn2d.py:146-149,
+    op/fused_act.py:87-94): the product's CPU-tensor branch is held to the fixtures written by the unmodified reference."""
+    import numpy as np
     import torch
 
-    from maua_stylegan2_b200 import _lib as L
     from maua_stylegan2_b200 import op
 
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ops_golden.npz"))
+    for name in g["ufd_names"]:
+        x, k, cfg, y = g[f"ufd_{name}_x"], g[f"ufd_{name}_k"], g[f"ufd_{name}_cfg"], g[f"ufd_{name}_y"]
+        up, down, p0, p1 = [int(v) for v in cfg]
+        out = op.upfirdn2d(torch.from_numpy(x), torch.from_numpy(k), up=up, down=down, pad=(p0, p1)).numpy()
+        assert out.shape == y.shape, name
+        np.testing.assert_allclose(out, y, rtol=0, atol=2e-6 * max(1.0, np.abs(y).max()), err_msg=name)
+    for name in ("fl2d", "fl4d", "fl4d_big"):
+        out = op.fused_leaky_relu(torch.from_numpy(g[f"{name}_x"]), torch.from_numpy(g[f"{name}_b"])).numpy()
+        np.testing.assert_allclose(out, g[f"{name}_y"], rtol=1e-6, atol=1e-7)
+    act = op.FusedLeakyReLU(6)
+    with torch.no_grad():
+        act.bias.copy_(torch.from_numpy(g["fl4d_b"]))
+        np.testing.assert_allclose(act(torch.from_numpy(g["fl4d_x"])).numpy(), g["fl4d_y"], rtol=1e-6, atol=1e-7)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """The CUDA branch has no fallback: without libmaua_b200.so the binding raises instead of computing elsewhere."""
+    from maua_stylegan2_b200 import _lib as L
+
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "libmaua_b200.so"))
     with pytest.raises(L.MauaError):
-        op.upfirdn2d(torch.zeros(1, 1, 4, 4), torch.ones(4, 4))
+        L.lib()
     with pytest.raises(L.MauaError):
-        op.fused_leaky_relu(torch.zeros(2, 3), torch.zeros(3))
+        L.call("maua_upfirdn2d_f32")
 
 
 def test_state_dict_keys_match_reference_layout():

@@ -3,12 +3,14 @@ reference, and vs the CPU oracle at BASELINE.json's config[0] shape (256x256, ch
 
 Metric (fixed once): max|a-b| / max|ref| per tensor, for the image and every activation map.
 Tolerance: 1e-3 (north_star); the fp32 SIMT path is held to 2e-5, the 3-product tensor-core path to 3e-4."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import stylegan2_oracle as O
-from tests.util import golden_inputs, make_generator, rel_err, strided
+from tests.util import GOLDEN, golden_inputs, make_generator, rel_err, strided
 
 pytestmark = pytest.mark.gpu
 
@@ -152,6 +154,70 @@ def test_generator_1024_configf_vs_oracle():
     e1, e2 = rel_err(img.cpu().numpy(), ref_img.numpy()), rel_err(img2.cpu().numpy(), ref_img.numpy())
     print(f"1024 tc: image {e1:.2e} / fused {e2:.2e} acts {['%.1e' % e for e in errs]}")
     assert max(errs) < TOL["tc"] and e1 < TOL["tc"] and e2 < TOL["tc"]
+
+
+@pytest.mark.parametrize("batch", [8, 16])
+def test_generator_1024_bench_batches_vs_oracle(batch):
+    """The MEASURED configurations: BASELINE configs[1] (batch 8, what bench.py times) and configs[2] (batch 16).  The tile
+    policy of the conv kernels is batch dependent (wide32 needs 16*B >= 120 items, the n_ctas < 120 fallbacks flip with
+    B), so the full batch runs through the product and two strided samples of it are checked against the CPU oracle —
+    every activation map and the image — plus the fused (no activation maps) path and the uint8 frames bench.py emits."""
+    size, cm, seed = 1024, 2, 0
+    g, sd = make_generator(size, cm, seed, "tc")
+    log_size, num_layers, n_latent = O.layout(size)
+    rng = np.random.Generator(np.random.PCG64(100 + batch))
+    latent = torch.from_numpy(rng.standard_normal((batch, n_latent, 512)).astype(np.float32)) * 0.5
+    noise = [torch.from_numpy(rng.standard_normal((batch, 1, 2 ** ((l + 5) // 2), 2 ** ((l + 5) // 2))).astype(np.float32))
+             if 2 ** ((l + 5) // 2) <= 256 else None for l in range(num_layers)]   # default hooks: buffers above 256
+    psi = torch.from_numpy(rng.uniform(0.6, 1.0, batch).astype(np.float32))
+    tl = torch.from_numpy(rng.standard_normal((1, 512)).astype(np.float32)) * 0.1
+    pick = [1, batch - 3]
+    with torch.no_grad():
+        g.truncation_latent = tl.cuda()
+        dn = [n.cuda() if n is not None else None for n in noise]
+        img, acts = g(latent.cuda(), noise=dn, truncation=psi.cuda(), input_is_latent=True, randomize_noise=False,
+                      return_activation_maps=True)
+        acts = [a[pick].cpu() for a in acts]
+        img = img[pick].cpu()
+        fused, _ = g(latent.cuda(), noise=dn, truncation=psi.cuda(), input_is_latent=True, randomize_noise=False)
+        fused = fused[pick].cpu()
+        u8, _ = g(latent.cuda(), noise=dn, truncation=psi.cuda(), input_is_latent=True, randomize_noise=False,
+                  return_u8=True)
+        u8 = u8[pick].cpu().numpy()
+        torch.cuda.empty_cache()
+        ref_img, ref_acts = O.generator_forward(sd, size, latent[pick], [n[pick] if n is not None else None for n in noise],
+                                                psi[pick], tl, channel_multiplier=cm)
+    errs = [rel_err(a.numpy(), r.numpy()) for a, r in zip(acts, ref_acts)]
+    e1, e2 = rel_err(img.numpy(), ref_img.numpy()), rel_err(fused.numpy(), ref_img.numpy())
+    print(f"1024 tc batch {batch}: image {e1:.2e} / fused {e2:.2e} acts {['%.1e' % e for e in errs]}")
+    assert max(errs) < TOL["tc"] and e1 < TOL["tc"] and e2 < TOL["tc"]
+    diff = np.abs(u8.astype(np.int32) - O.frames_to_u8(ref_img).astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3   # truncation to uint8 can flip a byte where fp32 differs by 1e-4
+
+
+@pytest.mark.parametrize("impl", ["tc"])
+def test_generator_1024_matches_reference_golden(impl):
+    """BASELINE configs[1] architecture against the UNMODIFIED reference's own CPU output (tests/golden/generator_g1024.npz,
+    written by make_golden.py --g1024): strided activation maps, strided image and a full-resolution centre crop."""
+    from tests.test_oracle_golden import regenerate_noise
+
+    gold = np.load(os.path.join(GOLDEN, "generator_g1024.npz"))
+    size, cm, seed = int(gold["size"]), int(gold["cm"]), int(gold["seed"])
+    g, sd = make_generator(size, cm, seed, impl)
+    noise = regenerate_noise(gold, size, seed)
+    g.truncation_latent = torch.from_numpy(gold["truncation_latent"]).cuda()
+    with torch.no_grad():
+        img, acts = g(torch.from_numpy(gold["latent"]).cuda(), noise=[n.cuda() if n is not None else None for n in noise],
+                      truncation=torch.from_numpy(gold["psi"]).cuda(), input_is_latent=True, randomize_noise=False,
+                      return_activation_maps=True)
+    st, c0 = int(gold["image_stride"]), size // 2 - 64
+    amax = float(gold["image_absmax"])
+    img = img.cpu().numpy()
+    e_img = max(np.abs(img[:, :, ::st, ::st] - gold["image"]).max(),
+                np.abs(img[:, :, c0:c0 + 128, c0:c0 + 128] - gold["image_crop"]).max()) / amax
+    errs = [float(np.abs(strided(a) - gold[f"act_{l}"]).max() / float(gold[f"act_{l}_absmax"])) for l, a in enumerate(acts)]
+    print(f"1024 golden {impl}: image {e_img:.2e} acts {['%.1e' % e for e in errs]}")
+    assert e_img < TOL[impl] and max(errs) < TOL[impl]
 
 
 def test_generator_512_confige_bend_and_truncation_sweep():

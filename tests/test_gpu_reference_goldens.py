@@ -1,7 +1,7 @@
-"""GPU parity cases written AFTER this round's GPU budget was spent: they have not run on a B200 yet, so they are
-non-strict xfail (XPASS when green, never a suite failure) and sorted last.  Each compares the product path directly with
-fixtures produced by the UNMODIFIED reference (tests/golden/make_golden.py); the oracle is already green on all of them
-(tests/test_oracle_golden.py).  Round 2: run them, drop the marker."""
+"""Product path vs fixtures produced by the UNMODIFIED reference (tests/golden/make_golden.py): the 256^2 cm=2 generator
+(BASELINE configs[0] architecture), `--noconst` LatentInput, shape-changing bends at layers 0/2/5, and the get_rewrites
+contract through the frame loop.  (First ran on a B200 at the end of round 1 as non-strict xfail — all XPASS; the marker
+is gone: a regression here now fails the suite.)  The oracle is held to the same fixtures in tests/test_oracle_golden.py."""
 import os
 
 import numpy as np
@@ -11,8 +11,7 @@ import torch
 from oracle import stylegan2_oracle as O
 from tests.util import GOLDEN, rel_err, strided
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: not yet run on a B200")]
+pytestmark = pytest.mark.gpu
 
 
 def _generator(size, cm, sd, impl, constant_input=True):

@@ -122,6 +122,118 @@ def test_tc_conv_matches_fp64_reference(b, cin, cout, h, w, up):
         assert torch.equal(u2, u3)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# The persistent halo kernel (v2, csrc/modconv_tc2.cu) — the kernel that carries ~85 % of the conv time of the bench.
+# It only takes layers with a GEMM grid >= 64 x 32 (or the wide 32^2 case), which the small cases above never reach.
+# ---------------------------------------------------------------------------------------------------------------
+V2_CASES = [
+    # b, cin, cout, h, w, up          what the default tile policy picks (asserted through maua_modconv_tc_last_config)
+    (8, 512, 512, 32, 32, False),    # "wide32": R=1 BN=256 needs 16*B >= 120 items
+    (2, 128, 128, 256, 256, False),  # R=2 BN=128 (3 MMAs per K-step)
+    (1, 32, 32, 1024, 1024, False),  # R=4 BN=32 concat, weights resident in shared memory
+    (2, 64, 64, 128, 96, False),     # BN=64 concat, non-square
+    (1, 256, 256, 64, 64, False),    # BN=256, few items -> policy fallbacks (n_ctas < 120)
+    (2, 64, 32, 512, 512, True),     # up, BN=32 concat, 4 phases in one item
+    (2, 128, 64, 256, 256, True),    # up, R=2 BN=64, 2 phase groups
+    (2, 256, 128, 128, 128, True),   # up, BN=128, 2 phase groups
+    (1, 512, 256, 64, 64, True),     # up, BN=256, 4 phase groups (one phase per item)
+    (3, 64, 48, 70, 40, False),      # Cout not a power of two (BN=16), ragged tiles
+]
+
+
+def _case_tensors(b, cin, cout, h, w, up, seed):
+    torch.manual_seed(seed)
+    x = torch.randn(b, cin, h, w, device="cuda")
+    wt = torch.randn(cout, cin, 3, 3, device="cuda")
+    s = 1 + 0.5 * torch.randn(b, cin, device="cuda")
+    d = 0.5 + torch.rand(b, cout, device="cuda")
+    oh, ow = (2 * h, 2 * w) if up else (h, w)
+    noise = torch.randn(b, 1, oh, ow, device="cuda")
+    nw = torch.tensor([0.3], device="cuda")
+    bias = 0.1 * torch.randn(cout, device="cuda")
+    s_next = 1 + 0.5 * torch.randn(b, cout, device="cuda")
+    return x, wt, s, d, noise, nw, bias, s_next, 1 / (cin * 9) ** 0.5
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w,up", V2_CASES)
+def test_tc2_halo_kernel_matches_fp64_reference(b, cin, cout, h, w, up):
+    from maua_stylegan2_b200 import _lib as L
+
+    x, wt, s, d, noise, nw, bias, s_next, scale = _case_tensors(b, cin, cout, h, w, up, b * 1000 + cin + cout + h)
+    ref, raw = _reference(x, wt, s, d, noise, nw, bias, up, scale)
+    y, o_hi, o_lo, u = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 3, scale)
+    cfg = L.last_conv_config()
+    assert cfg.startswith("v2 "), f"{(b, cin, cout, h, w, up)} was routed to {cfg!r}, not to the halo kernel"
+    print(cfg)
+    _check(ref, raw, y, o_hi, o_lo, u, s_next, up)
+    y2, o_hi2, o_lo2, u2 = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 3, scale)
+    assert torch.equal(y, y2) and torch.equal(o_hi, o_hi2) and torch.equal(o_lo, o_lo2), "v2 must be deterministic"
+
+
+# Forced configurations "R,BN,cat,groups": every tap table of modconv_tc2.cu (c_taps[0..7] = same-res; up with 1 / 2 / 4
+# phase groups), both product modes (three N=BN MMAs / concat) and every R, on shapes small enough for the fp64 reference.
+FORCED = [
+    ((2, 64, 32, 64, 40, False), ["1,32,0,1", "2,32,0,1", "4,32,0,1", "1,32,1,1", "2,16,1,1", "4,32,1,1", "4,16,0,1"]),
+    ((2, 64, 64, 48, 24, False), ["1,64,0,1", "2,64,1,1", "1,32,1,1"]),
+    ((1, 128, 256, 32, 32, False), ["1,256,0,1", "2,128,0,1", "1,128,0,1"]),
+    ((2, 64, 32, 56, 24, True), ["1,32,0,1", "1,32,1,1", "2,32,0,1", "1,32,0,2", "2,32,1,2", "4,32,0,2", "1,32,0,4",
+                                 "2,32,1,4", "4,32,0,4", "4,16,1,4"]),
+    ((1, 128, 128, 32, 32, True), ["1,128,0,1", "1,128,0,2", "2,128,0,4", "1,64,1,2"]),
+    ((1, 64, 256, 33, 17, True), ["1,256,0,4", "1,256,0,2", "2,128,0,2"]),
+]
+
+
+@pytest.mark.parametrize("case,forces", FORCED)
+def test_tc2_forced_configurations(case, forces, monkeypatch):
+    from maua_stylegan2_b200 import _lib as L
+
+    b, cin, cout, h, w, up = case
+    x, wt, s, d, noise, nw, bias, s_next, scale = _case_tensors(b, cin, cout, h, w, up, 77 + cin + h)
+    ref, raw = _reference(x, wt, s, d, noise, nw, bias, up, scale)
+    for f in forces:
+        monkeypatch.setenv("MAUA_TC_FORCE", f)
+        y, o_hi, o_lo, u = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 3, scale)
+        cfg = L.last_conv_config()
+        r, bn, cat, groups = (int(v) for v in f.split(","))
+        assert f"v2 up={int(up)} R={r} BN={bn} cat={cat} groups={groups} " in cfg, (f, cfg)
+        _check(ref, raw, y, o_hi, o_lo, u, s_next, up)
+    monkeypatch.delenv("MAUA_TC_FORCE")
+    # an infeasible forced configuration is an error, never a silent fallback to another kernel
+    monkeypatch.setenv("MAUA_TC_FORCE", "4,256,1,1")
+    with pytest.raises(L.MauaError):
+        _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 3, scale)
+
+
+def test_tc2_fused_torgb_partial_sums():
+    """Fused ToRGB epilogue (Cout <= 128, same-res): rgb_out[b,k] = sum_c rgb_w[b,k,c] * act[b,c]."""
+    from maua_stylegan2_b200 import _lib as L
+    from maua_stylegan2_b200.synthesis import _modulate_split
+
+    for (b, cin, cout, h, w) in ((2, 64, 32, 128, 64), (1, 128, 128, 64, 64), (2, 64, 64, 80, 40)):
+        x, wt, s, d, noise, nw, bias, s_next, scale = _case_tensors(b, cin, cout, h, w, False, 5 + cout)
+        ref, _ = _reference(x, wt, s, d, noise, nw, bias, False, scale)
+        rgb_w = torch.randn(b, 3, cout, device="cuda")
+        w_hi, w_lo = _pack(wt, scale)
+        hi, lo = _modulate_split(x, x[0].numel(), s, b)
+        rgb = torch.full((b, 3, h, w), float("nan"), device="cuda")
+        o_hi = torch.zeros((b, h, w, cout), device="cuda", dtype=torch.bfloat16)
+        o_lo = torch.zeros_like(o_hi)
+        ep = L.ConvEpilogue()
+        ep.d, ep.noise, ep.noise_weight, ep.noise_bstride = d.data_ptr(), noise.data_ptr(), nw.data_ptr(), h * w
+        ep.bias, ep.s_next = bias.data_ptr(), s_next.data_ptr()
+        ep.out_hi, ep.out_lo = o_hi.data_ptr(), o_lo.data_ptr()
+        ep.rgb_w, ep.rgb_out = rgb_w.data_ptr(), rgb.data_ptr()
+        ep.slope, ep.act_scale, ep.activate = 0.2, 2 ** 0.5, 1
+        L.call("maua_modconv_tc", hi.data_ptr(), lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), C.byref(ep), b, cin, cout,
+               h, w, 0, 3, L.stream_ptr(x.device))
+        torch.cuda.synchronize()
+        assert L.last_conv_config().startswith("v2 ")
+        want = torch.einsum("bkc,bchw->bkhw", rgb_w.double().cpu(), ref)
+        assert rel_err(rgb.cpu().numpy(), want.numpy()) < 2e-4
+        rec = (o_hi.float() + o_lo.float()).permute(0, 3, 1, 2).cpu().double() / s_next.cpu().double()[:, :, None, None]
+        assert rel_err(rec.numpy(), ref.numpy()) < 3e-4
+
+
 def _check(ref, raw, y, o_hi, o_lo, u, s_next, up):
     if up:
         assert rel_err(u.cpu().numpy(), raw.numpy()) < 2e-4, "raw transposed-conv phases"

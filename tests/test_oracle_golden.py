@@ -67,7 +67,8 @@ def regenerate_noise(g, size, seed):
     return noise
 
 
-@pytest.mark.parametrize("fname", ["generator_g32.npz", "generator_g128.npz", "generator_g256.npz"])
+@pytest.mark.parametrize("fname", ["generator_g32.npz", "generator_g128.npz", "generator_g256.npz",
+                                   "generator_g1024.npz"])
 def test_generator_oracle_matches_reference(golden_dir, fname):
     g = _load(golden_dir, fname)
     size, cm, seed = int(g["size"]), int(g["cm"]), int(g["seed"])
@@ -82,9 +83,16 @@ def test_generator_oracle_matches_reference(golden_dir, fname):
         np.testing.assert_allclose(w.numpy(), g["w"], rtol=1e-4, atol=1e-5)
         image, acts = O.generator_forward(sd, size, torch.from_numpy(g["latent"]), noise, torch.from_numpy(g["psi"]),
                                           torch.from_numpy(g["truncation_latent"]), channel_multiplier=cm)
-    scale = np.abs(g["image"]).max()
-    assert np.abs(image.numpy() - g["image"]).max() <= 2e-5 * scale
     from tests.golden.make_golden import strided
+
+    if "image_stride" in g.files:   # 1024^2 fixture: strided image + full-resolution centre crop
+        st, c0, scale = int(g["image_stride"]), size // 2 - 64, float(g["image_absmax"])
+        im = image.numpy()
+        assert np.abs(im[:, :, ::st, ::st] - g["image"]).max() <= 2e-5 * scale
+        assert np.abs(im[:, :, c0:c0 + 128, c0:c0 + 128] - g["image_crop"]).max() <= 2e-5 * scale
+    else:
+        scale = np.abs(g["image"]).max()
+        assert np.abs(image.numpy() - g["image"]).max() <= 2e-5 * scale
 
     for l, a in enumerate(acts):
         ref = g[f"act_{l}"]

@@ -6,7 +6,6 @@ import ctypes as C
 import os
 import sys
 
-os.environ["MAUA_TC_TUNE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
