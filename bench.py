@@ -30,6 +30,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SIZE, CM, FPS, AUDIO_S = 1024, 2, 30, 30
+DEFAULT_PRECISION = "bf16x3"
+DTYPES = {"bf16x3": "bf16x3 (split-bf16 tensor-core products hi*hi + hi*lo + lo*hi, fp32 accumulate; fp32-grade: network "
+                    "error ~5e-5 of the tensor max)",
+          "mixed": "bf16x3 below 512^2; fp16 activations x fp16 (hi, lo) weight pair at >= 512^2 (one tensor-core pass, fp32 "
+                   "accumulate; network error ~5e-4 of the tensor max, parity bar 1e-3)",
+          "bf16": "bf16 (single product, fast preview)"}
 CONV_GFLOP_PER_FRAME = 148.52  # BASELINE.md §3 (2*MAC, algorithmic)
 
 
@@ -250,8 +256,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--conv", default="tc", choices=["tc", "simt"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--precision", default=DEFAULT_PRECISION, choices=["bf16x3", "mixed", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -304,35 +311,46 @@ def main():
                       truncation=1.0, input_is_latent=True, randomize_noise=False, return_u8=True)
         return frames
 
-    def step(i):
-        frames = step_local(i)
-        if gather is not None:
-            work, out = gather(frames, i & 1)
-            work.wait()
-            return out
-        return frames
-
     def barrier():
         if world > 1:
             dist.barrier()
 
+    def pipeline_run(lat, nz, n_steps, offset, to_host):
+        """K steps of the public frame loop (render.FramePipeline: CUDA-graph replay of the captured forward, rank-strided
+        batches, one all-gather per step on NCCL's stream — the compute stream never waits for it).  Graph capture and
+        first-touch setup happen in warmup(), outside the timed region.  Returns (device ms, wall s, pipe)."""
+        lo = offset * B * world
+        idx = torch.tensor([j % n_frames for j in range(lo, lo + n_steps * B * world)]).to(lat.device)
+        pipe = FramePipeline(g, lat[idx], [x[idx] if x is not None else None for x in nz], B, truncation=1.0, rank=rank,
+                             world=world)
+        if to_host and rank == 0:
+            pipe.prepare_host_buffers((SIZE, SIZE, 3))
+        pipe.warmup()
+        sink_bytes = [0]
+
+        def consume(frames):
+            sink_bytes[0] += int(frames[:, ::64, ::64].sum()) * 0 + frames.nbytes  # touch the host frames
+
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        pipe.run(consume if (to_host and rank == 0) else None, gather)
+        e1.record()      # (run() makes the compute stream wait for the last collectives before returning)
+        torch.cuda.synchronize()
+        barrier()
+        return e0.elapsed_time(e1), time.perf_counter() - t0, pipe
+
     with torch.no_grad():
         sampler = ClockSampler(local_rank) if rank == 0 else None
-        for i in range(args.warmup):
-            step(i)
-        torch.cuda.synchronize()
-        barrier()
+        # ---- value: inputs resident in HBM, exactly K steps, CUDA events, max over ranks --------------------------
+        pipeline_run(latents_d, noise_d, args.warmup, 0, False)
         l0 = L.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args.steps):
-            step(args.warmup + i)
-        e1.record()
-        torch.cuda.synchronize()
-        barrier()
-        launches = L.launch_count() - l0
+        ms_dev, _, vpipe = pipeline_run(latents_d, noise_d, args.steps, args.warmup, False)
+        launches = vpipe.kernels_per_step * args.steps
         clocks = sampler.stop() if sampler else None
-        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        ms = torch.tensor([ms_dev], device=device)
         lt = torch.tensor([float(launches)], device=device)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -341,30 +359,8 @@ def main():
         value = args.steps * B * world / (ms_total / 1000.0)
 
         # ---- e2e through the public frame loop (host buffers, H2D + D2H inside the timed region) -----------------
-        def e2e_run(n_steps, offset):
-            lo = offset * B * world
-            hi = lo + n_steps * B * world
-            idx = [j % n_frames for j in range(lo, hi)]
-            pipe = FramePipeline(g, latents_h[idx], [x[idx] if x is not None else None for x in noise_h], B,
-                                 truncation=1.0, rank=rank, world=world)
-            if rank == 0:
-                pipe.prepare_host_buffers((SIZE, SIZE, 3))
-            pipe.warmup()  # graph capture / first-touch setup is not part of the steady-state frame loop
-            sink_bytes = [0]
-
-            def consume(frames):
-                sink_bytes[0] += int(frames[:, ::64, ::64].sum()) * 0 + frames.nbytes  # touch the host frames
-
-            torch.cuda.synchronize()
-            barrier()
-            t0 = time.perf_counter()
-            pipe.run(consume if rank == 0 else None, gather)
-            torch.cuda.synchronize()
-            barrier()
-            return time.perf_counter() - t0, pipe
-
-        e2e_run(args.warmup, 0)
-        dt, pipe = e2e_run(args.steps, args.warmup)
+        pipeline_run(latents_h, noise_h, args.warmup, 0, True)
+        _, dt, pipe = pipeline_run(latents_h, noise_h, args.steps, args.warmup, True)
         dtt = torch.tensor([dt], device=device)
         if world > 1:
             dist.all_reduce(dtt, op=dist.ReduceOp.MAX)
@@ -386,7 +382,7 @@ def main():
             ev = L.PROFILE["events"]
             L.PROFILE = None
             tot = {}
-            conv_ms, conv_fl = 0.0, 0.0
+            conv_ms, conv_fl, conv_issued = 0.0, 0.0, 0.0
             per_layer = {}
             for name, tag, s, e in ev:
                 t = s.elapsed_time(e)
@@ -394,6 +390,7 @@ def main():
                 if name in ("maua_modconv_tc", "maua_modconv_simt_f32") and tag is not None:
                     conv_ms += t
                     conv_fl += tag["flops"]
+                    conv_issued += tag["flops"] * tag.get("nprod", 1)
                     key = f"L{tag['layer']}:{tag['cin']}->{tag['cout']}@{tag['h']}{'up' if tag['up'] else ''}"
                     a = per_layer.setdefault(key, [0.0, 0.0])
                     a[0] += t
@@ -401,14 +398,17 @@ def main():
             shares = {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}
             if conv_ms > 0:
                 ach = conv_fl / (conv_ms * 1e-3) / 1e12
-                nprod = 3 if (args.precision == "bf16x3" and args.conv == "tc") else 1
+                nprod = 3 if (args.precision in ("bf16x3", "mixed") and args.conv == "tc") else 1
                 roof = {"kernel": "maua_modconv_tc" if args.conv == "tc" else "maua_modconv_simt_f32", "bound": "tensor",
                         "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": ach / pk["bf16_tflops_sustained"], "traffic": ncu_traffic("maua_modconv_tc") if args.conv == "tc" and B == 8 else None,
-                        "traffic_unit": "bytes of DRAM read+write per launch set (17 conv launches of one batch-8 step), ncu",
+                        "traffic_unit": "bytes of DRAM read+write per launch set (17 conv launches of one batch-8 step)",
+                        "traffic_source": "committed `ncu --set full` capture of this same step (profiles/*_traffic.json, "
+                                          "tools/collect_profiles.py) — not measured live by this run",
                         "peak_source": pk["source"] + " sustained bf16",
                         "algorithmic_gflop_per_launch_set": conv_fl / nprof / 1e9,
-                        "products_per_mac": nprod, "issued_frac": nprod * ach / pk["bf16_tflops_sustained"],
+                        "products_per_mac": nprod if args.precision != "mixed" else "3 below 512^2, 2 (fp16 a*(w_hi+w_lo)) at >= 512^2",
+                        "issued_frac": conv_issued / (conv_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
                         "ms_per_step": conv_ms / nprof,
                         "per_layer_tflops": {k: round(v[1] / (v[0] * 1e-3) / 1e12, 2) for k, v in per_layer.items()},
                         "per_layer_ms": {k: round(v[0] / nprof, 4) for k, v in per_layer.items()}}
@@ -436,6 +436,27 @@ def main():
                         "shape": f"[{bb},32,2049,2049]->[{bb},32,2048,2048] fp32 (in+out {by / 1e9:.2f} GB > L2)"}
             del x, y
 
+    # ---- GPU comparator (SURVEY §8(d) / BASELINE.md §4.5): the reference's own CUDA path — its compiled op/ extension
+    # (oracle/_ref) + cuDNN grouped convs on per-sample modulated weights — on this same GPU, after (never inside) the repo
+    # arm's timed regions.  Reported next to cpu_baseline; not the target, the honest comparator.
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        try:
+            from oracle import gpu_reference as GR
+
+            torch.cuda.empty_cache()
+            r = GR.time_forward(SIZE, CM, B, steps=3, warmup=2)
+            gpu_ref = {"unit": "frames/s", "batch": B,
+                       "tf32": round(r["tf32"]["frames_per_s"], 2), "fp32": round(r["fp32"]["frames_per_s"], 2),
+                       "ms_per_step_tf32": round(r["tf32"]["ms_per_step"], 2),
+                       "ms_per_step_fp32": round(r["fp32"]["ms_per_step"], 2),
+                       "what": "reference CUDA path on this GPU: oracle/_ref upfirdn2d + fused_bias_act extensions (the "
+                               "reference's own op/*.cu) + cuDNN grouped F.conv2d / F.conv_transpose2d (groups = batch) on "
+                               "materialised per-sample weights, models/stylegan2.py:217-254; cudnn.benchmark on; "
+                               "tf32 = torch default cudnn.allow_tf32, fp32 = allow_tf32 off"}
+        except Exception as e:  # oracle/_ref absent: say so instead of inventing a number
+            gpu_ref = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_port_run(steps=2, warmup=1, budget_s=40.0)
@@ -446,11 +467,10 @@ def main():
         line = {"metric": "1024x1024 frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16x3 (split-bf16 tensor-core products, fp32 accumulate; fp32-grade)" if args.precision == "bf16x3" and args.conv == "tc"
-                else ("bf16" if args.conv == "tc" else "f32"),
+                "dtype": DTYPES[args.precision] if args.conv == "tc" else "f32",
                 "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(lt.item()), "roofline": roof, "roofline_upfirdn2d": roof_ufd,
-                "kernel_ms_per_step": shares, "cpu_baseline": cpu,
+                "kernel_ms_per_step": shares, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
                 "conv_gflop_per_frame": CONV_GFLOP_PER_FRAME}
         _emit(line)
     if world > 1:

@@ -25,6 +25,7 @@
  *   maua_blur_act_nhwc        <- Blur.forward + NoiseInjection + FusedLeakyReLU           models/stylegan2.py:89-92,262-266
  *   maua_noise_bias_act_f32   <- NoiseInjection.forward + FusedLeakyReLU.forward models/stylegan2.py:262-266, op/fused_act.py:82-97
  *   maua_torgb_f32            <- ToRGB.forward (1x1 modconv + bias + Upsample(skip))      models/stylegan2.py:356-365
+ *   maua_synth_forward        <- Generator.forward (synthesis network, one call per batch)  models/stylegan2.py:537-576
  *   maua_rgb_to_u8_nhwc       <- render.split_batches clamp/scale/permute/astype(uint8)   render.py:40-43
  *   maua_fit_frames_u8        <- 2048-wide frames cropped + PIL-resized to 1920x1080             render.py:98-105
  *   maua_bend_warp_f32        <- Translate / Zoom / Rotate network bends                  audioreactive/bend.py:51-102
@@ -45,7 +46,7 @@ extern "C" {
 #define MAUA_E_CUDA (-2)     /* CUDA runtime / driver error (launch, tensor-map encode, ...) */
 #define MAUA_E_UNSUPPORTED (-3)
 
-#define MAUA_ABI_VERSION 1
+#define MAUA_ABI_VERSION 2
 
 int maua_abi_version(void);
 const char* maua_last_error(void);
@@ -91,6 +92,11 @@ typedef struct MauaStyleJob {
   const float* wsq;   /* [cout, cin] = w_scale^2 * sum_k W^2, or NULL when demodulate=False */
   float* s_out;       /* [batch, cin]  */
   float* d_out;       /* [batch, cout] (ignored when wsq == NULL) */
+  /* Optional range normalisation for consumers that store x * s in fp16 (the "f16" activation format): when not NULL
+   * (and wsq != NULL), s_norm_out[b,:] = s[b,:] * 2^-e_b and d_out[b,:] is multiplied by 2^e_b, with e_b the smallest
+   * integer such that max_ci |s[b,ci]| < 2^e_b.  Powers of two: conv(x * s) * d is unchanged bit for bit, but
+   * |x * s_norm| <= |x|, so trained checkpoints with large styles cannot push the fp16 operand past 65504. */
+  float* s_norm_out;  /* [batch, cin] or NULL */
   int32_t cin;
   int32_t cout;
   int32_t latent_index; /* which W+ row feeds this layer */
@@ -100,7 +106,7 @@ typedef struct MauaStyleJob {
 /* For every job j and sample b:
  *   w      = mean[:] + psi[b] * (latent[b, jobs[j].latent_index, :] - mean[:])      (psi NULL -> psi_scalar)
  *   s[b,:] = w @ (mod_w / sqrt(style_dim))^T + mod_b
- *   d[b,:] = rsqrt( sum_ci s[b,ci]^2 * wsq[:,ci] + 1e-8 )
+ *   d[b,:] = rsqrt( sum_ci s[b,ci]^2 * wsq[:,ci] + 1e-8 )          (* 2^e_b when s_norm_out is given, see above)
  * `jobs` is a DEVICE array of n_jobs MauaStyleJob.  latent: [batch, n_latent, style_dim]; mean: [style_dim] or NULL
  * (NULL = no truncation).  latent_trunc_out (may be NULL): [batch, n_latent, style_dim] truncated latents. */
 int maua_style_prologue_f32(const MauaStyleJob* jobs, int n_jobs, const float* latent, const float* mean,
@@ -160,6 +166,17 @@ int maua_pack_weight_bf16x2(const float* w, void* w_hi, void* w_lo, int cout, in
 int maua_modulate_split_nhwc(const float* x, long long x_bstride, const float* s, void* x_hi, void* x_lo, int batch,
                              int ch, int h, int w, void* stream);
 
+/* The "f16" activation format (n_products == 2 of maua_modconv_tc): ONE fp16 plane per activation (11-bit mantissa,
+ * saturating conversion) and weights as an fp16 (hi, lo) pair (22 bits: exact for practical purposes), so a modulated
+ * conv costs one tensor-core pass over the activations instead of three.  Measured network-level error of rounding the
+ * activations of the four >= 512^2 layers of the 1024^2 generator to fp16: 4.8e-4 of the tensor max (tools/exp_precision.py)
+ * — inside the 1e-3 parity bar, 10x closer to fp32 than the reference's own default GPU path (TF32 cuDNN convs, 5e-3). */
+int maua_pack_weight_f16x2(const float* w, void* w_hi, void* w_lo, int cout, int cin, int ksize, float w_scale,
+                           void* stream);
+/* x [B,C,H,W] fp32 * s[b,c] -> x_f16 [B,H,W,C] fp16 (one plane). s may be NULL. */
+int maua_modulate_f16_nhwc(const float* x, long long x_bstride, const float* s, void* x_f16, int batch, int ch, int h,
+                           int w, void* stream);
+
 typedef struct MauaConvEpilogue {
   const float* d;            /* [B,Cout] demod or NULL                                                    */
   const float* noise;        /* [B or 1, H_out, W_out] or NULL                                            */
@@ -174,7 +191,7 @@ typedef struct MauaConvEpilogue {
   float slope;               /* leaky-relu slope (0.2)                                                    */
   float act_scale;           /* sqrt(2)                                                                   */
   int32_t activate;          /* 0: linear (no noise/bias/act), 1: noise+bias+lrelu                        */
-  int32_t reserved;
+  int32_t out_fmt;           /* format of out_hi/out_lo: 0 = bf16 (hi, lo) pair, 1 = ONE fp16 plane in out_hi      */
   /* Optional fused ToRGB partial sums (same-resolution layers whose whole Cout fits one N tile, Cout <= 128):
    * rgb_out[b,k,y,x] = sum_c rgb_w[b,k,c] * act[b,c,y,x]  (no bias / skip: see maua_rgb_finish_f32).            */
   const float* rgb_w;        /* [B,3,Cout] = w_scale * Wrgb[k,c] * s_rgb[b,c] (maua_rgb_weights_f32) or NULL     */
@@ -186,6 +203,8 @@ typedef struct MauaConvEpilogue {
 } MauaConvEpilogue;
 
 /* 3x3 modulated conv on the tensor cores.  x_hi/x_lo [B,H,W,Cin] bf16 (pre-scaled by s), w_hi/w_lo [9][Cout][Cin].
+ *   n_products: 3 = split bf16 (hi*hi + hi*lo + lo*hi), 1 = bf16 hi*hi only (fast, ~1e-2),
+ *               2 = fp16: x_hi is ONE fp16 plane (x_lo ignored), w_hi/w_lo the fp16 pair (halo kernel only: H,W >= 64x32).
  *   up == 0: same resolution, zero pad 1, fused epilogue (demod, noise, bias, lrelu, next-style, split)
  *   up == 1: stride-2 transposed conv evaluated as 4 sub-pixel phases; writes ep->out_raw_nhwc (demod applied).
  * Requirements: Cin % 32 == 0, Cout % 16 == 0, Cout >= 16.  `ep` is a HOST pointer (copied at launch). */
@@ -197,6 +216,68 @@ int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w_hi, const 
  * epilogue of `ep` (noise, bias, lrelu, s_next, split / fp32 NCHW).  ep->d is ignored (already applied). */
 int maua_blur_act_nhwc(const float* u, const float* k4, const MauaConvEpilogue* ep_host, int batch, int ch, int hu,
                        int wu, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Whole-forward handle API: ONE call per batch = models/stylegan2.py:Generator.forward(styles, noise=..., truncation=...,
+ * input_is_latent=True, randomize_noise=False) on the tensor-core path (models/stylegan2.py:537-576), for host languages
+ * that bind the library directly (SURVEY.md §8(b) "Op ABI", last cell).  The handle is a host object; it owns no device
+ * memory: packed weights live in the caller's `plan` buffer, styles / activations in the caller's `workspace`.
+ *
+ *   maua_synth_create(desc, &h)                       describe the network (parameter pointers are borrowed, like a module)
+ *   maua_synth_prepare(h, plan, plan_bytes, stream)   Wsq + packed tensor-core weights; again after the weights change
+ *   maua_synth_bind(h, workspace, bytes, batch, st)   lay out the workspace for one batch size (synchronises; not capturable)
+ *   maua_synth_forward(h, ...)                        ~50 kernel launches on `stream`, no host synchronisation, capturable
+ *   maua_synth_destroy(h)
+ * Not covered (use the per-operator entry points, as maua_stylegan2_b200/synthesis.py does): network bends between
+ * layers, returning the activation maps, LatentInput (--noconst), layers outside the tensor-core shape set.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct MauaSynthLayer {      /* one StyledConv (+ the ToRGB that follows it, if any); all DEVICE pointers */
+  const float* conv_weight;          /* conv.weight             [1,Cout,Cin,3,3]                                  */
+  const float* mod_weight;           /* conv.modulation.weight  [Cin,style_dim]                                   */
+  const float* mod_bias;             /* conv.modulation.bias    [Cin]                                             */
+  const float* noise_weight;         /* noise.weight            [1]                                               */
+  const float* act_bias;             /* activate.bias           [Cout]                                            */
+  const float* noise_buffer;         /* noises.noise_i [1,1,H_out,W_out]: used when no per-frame noise is passed  */
+  const float* blur_kernel;          /* conv.blur.kernel [4,4] (up layers), else NULL                             */
+  const float* rgb_weight;           /* to_rgb.conv.weight [1,3,Cout,1,1] or NULL when no ToRGB follows           */
+  const float* rgb_mod_weight;       /* to_rgb.conv.modulation.weight [Cout,style_dim]                            */
+  const float* rgb_mod_bias;         /* to_rgb.conv.modulation.bias   [Cout]                                      */
+  const float* rgb_bias;             /* to_rgb.bias [1,3,1,1]                                                     */
+  const float* rgb_up_kernel;        /* to_rgb.upsample.kernel [4,4] (NULL for the first ToRGB: no skip)          */
+  int32_t cin, cout, up;             /* up: 1 = stride-2 transposed conv + blur (models/stylegan2.py:229-238)     */
+  int32_t latent_index;              /* W+ row of this conv                                */
+  int32_t rgb_latent_index;          /* W+ row of the ToRGB                                                       */
+  int32_t reserved;
+} MauaSynthLayer;
+
+typedef struct MauaSynthDesc {
+  const MauaSynthLayer* layers;      /* HOST array, copied by maua_synth_create                                   */
+  const float* const_input;          /* input.input [1,C,in_h,in_w] (ConstantInput)                               */
+  int32_t n_layers, in_h, in_w;      /* 2*log2(size)-3 layers; 4 x 4                                              */
+  int32_t style_dim, n_latent;       /* 512; 2*log2(size)-2                                                       */
+  int32_t precision;                 /* 0 = bf16x3, 1 = mixed (fp16 activations from f16_min_res on), 2 = bf16    */
+  int32_t f16_min_res;               /* 512                                                                       */
+  int32_t min_rgb_size;              /* Generator(min_rgb_size=4)                                                 */
+} MauaSynthDesc;
+
+typedef struct MauaSynth MauaSynth;
+
+int maua_synth_create(const MauaSynthDesc* desc_host, MauaSynth** out);
+void maua_synth_destroy(MauaSynth* h);
+size_t maua_synth_plan_bytes(const MauaSynth* h);
+int maua_synth_prepare(MauaSynth* h, void* plan, size_t plan_bytes, void* stream);
+size_t maua_synth_workspace_bytes(const MauaSynth* h, int batch);
+int maua_synth_bind(MauaSynth* h, void* workspace, size_t workspace_bytes, int batch, void* stream);
+/* latent [batch, latent_rows >= n_latent, style_dim]; noise: HOST array of n_layers device pointers (entry or array NULL
+ * -> the layer's noise_buffer), noise_bstride: HOST array (0 = one map for the batch, H*W = per-sample maps);
+ * mean_latent [style_dim] or NULL (no truncation), psi [batch] or NULL (-> psi_scalar).
+ * out_rgb [batch,3,H,W] fp32 and/or out_u8 [batch,H,W,3] (render.py:40-43 conversion); at least one. */
+int maua_synth_forward(MauaSynth* h, const float* latent, int latent_rows, const float* const* noise_host,
+                       const long long* noise_bstride_host, const float* mean_latent, const float* psi, float psi_scalar,
+                       int batch, float* out_rgb, uint8_t* out_u8, void* stream);
+/* [batch, n_latent, style_dim] truncated latents of the last forward (inside the bound workspace) */
+const float* maua_synth_truncated_latents(const MauaSynth* h);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Audio feature chain (cuFFT-fronted; replaces the librosa/scipy CPU path of audioreactive/signal.py:31-156 and the

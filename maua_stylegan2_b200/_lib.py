@@ -16,7 +16,7 @@ class MauaError(RuntimeError):
 class StyleJob(C.Structure):
     """MauaStyleJob (include/maua_b200.h)."""
     _fields_ = [("mod_w", C.c_void_p), ("mod_b", C.c_void_p), ("wsq", C.c_void_p), ("s_out", C.c_void_p),
-                ("d_out", C.c_void_p), ("cin", C.c_int32), ("cout", C.c_int32), ("latent_index", C.c_int32),
+                ("d_out", C.c_void_p), ("s_norm_out", C.c_void_p), ("cin", C.c_int32), ("cout", C.c_int32), ("latent_index", C.c_int32),
                 ("reserved", C.c_int32)]
 
 
@@ -25,8 +25,23 @@ class ConvEpilogue(C.Structure):
     _fields_ = [("d", C.c_void_p), ("noise", C.c_void_p), ("noise_weight", C.c_void_p), ("bias", C.c_void_p),
                 ("s_next", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_f32_nchw", C.c_void_p),
                 ("out_raw_nhwc", C.c_void_p), ("noise_bstride", C.c_longlong), ("slope", C.c_float),
-                ("act_scale", C.c_float), ("activate", C.c_int32), ("reserved", C.c_int32), ("rgb_w", C.c_void_p),
+                ("act_scale", C.c_float), ("activate", C.c_int32), ("out_fmt", C.c_int32), ("rgb_w", C.c_void_p),
                 ("rgb_out", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong)]
+
+
+class SynthLayer(C.Structure):
+    """MauaSynthLayer (include/maua_b200.h)."""
+    _fields_ = [(n, C.c_void_p) for n in ("conv_weight", "mod_weight", "mod_bias", "noise_weight", "act_bias",
+                                          "noise_buffer", "blur_kernel", "rgb_weight", "rgb_mod_weight", "rgb_mod_bias",
+                                          "rgb_bias", "rgb_up_kernel")] + \
+               [(n, C.c_int32) for n in ("cin", "cout", "up", "latent_index", "rgb_latent_index", "reserved")]
+
+
+class SynthDesc(C.Structure):
+    """MauaSynthDesc (include/maua_b200.h)."""
+    _fields_ = [("layers", C.POINTER(SynthLayer)), ("const_input", C.c_void_p)] + \
+               [(n, C.c_int32) for n in ("n_layers", "in_h", "in_w", "style_dim", "n_latent", "precision", "f16_min_res",
+                                         "min_rgb_size")]
 
 
 _p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
@@ -45,7 +60,9 @@ SIGNATURES = {
     "maua_rgb_weights_f32": [_p, _p, _p, _i, _i, _f, _p],
     "maua_rgb_finish_f32": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "maua_pack_weight_bf16x2": [_p, _p, _p, _i, _i, _i, _f, _p],
+    "maua_pack_weight_f16x2": [_p, _p, _p, _i, _i, _i, _f, _p],
     "maua_modulate_split_nhwc": [_p, _ll, _p, _p, _p, _i, _i, _i, _i, _p],
+    "maua_modulate_f16_nhwc": [_p, _ll, _p, _p, _i, _i, _i, _i, _p],
     "maua_modconv_tc": [_p, _p, _p, _p, C.POINTER(ConvEpilogue), _i, _i, _i, _i, _i, _i, _i, _p],
     "maua_blur_act_nhwc": [_p, _p, C.POINTER(ConvEpilogue), _i, _i, _i, _i, _p],
     "maua_audio_stft_f32": [_p, _ll, _p, _p, _i, _i, _i, _p],
@@ -68,12 +85,20 @@ SIGNATURES = {
     "maua_fit_frames_u8": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p],
     "maua_bend_warp_f32": [_p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "maua_perlin_noise": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "maua_synth_create": [C.POINTER(SynthDesc), C.POINTER(C.c_void_p)],
+    "maua_synth_prepare": [_p, _p, C.c_size_t, _p],
+    "maua_synth_bind": [_p, _p, C.c_size_t, _i, _p],
+    "maua_synth_forward": [_p, _p, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), _p, _p, _f, _i, _p, _p, _p],
 }
 _SPECIAL = {
     "maua_abi_version": (C.c_int, []),
     "maua_last_error": (C.c_char_p, []),
     "maua_launch_count": (C.c_longlong, []),
     "maua_modconv_tc_last_config": (C.c_char_p, []),
+    "maua_synth_destroy": (None, [C.c_void_p]),
+    "maua_synth_plan_bytes": (C.c_size_t, [C.c_void_p]),
+    "maua_synth_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "maua_synth_truncated_latents": (C.c_void_p, [C.c_void_p]),
 }
 
 _lib = None

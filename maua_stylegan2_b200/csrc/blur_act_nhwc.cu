@@ -107,7 +107,13 @@ __global__ void __launch_bounds__(256) blur_act_nhwc_kernel(const float* __restr
 #pragma unroll
       for (int i = 0; i < 4; ++i) ep.out_f32_nchw[(((long long)b * ch + cbase + i) * oh + oy) * ow + ox] = v[i];
     }
-    if (hi) {
+    if (hi && ep.out_fmt == 1) {   // "f16" activation format: one fp16 plane
+      const long long o = (((long long)b * oh + oy) * ow + ox) * ch + cbase;
+      uint2 ph;
+      ph.x = pack_f16x2_sat(v[0] * sn.x, v[1] * sn.y);
+      ph.y = pack_f16x2_sat(v[2] * sn.z, v[3] * sn.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out_hi) + o) = ph;
+    } else if (hi) {
       const float ss[4] = {sn.x, sn.y, sn.z, sn.w};
       __nv_bfloat16 h4[4], l4[4];
 #pragma unroll
@@ -261,7 +267,13 @@ __global__ void __launch_bounds__(128 * (16 / RPT), 2) blur_act_nhwc_tma_kernel(
         const long long plane = (long long)oh * ow;
         o[0] = v0; o[plane] = v1; o[2 * plane] = v2; o[3 * plane] = v3;
       }
-      if (hi) {
+      if (hi && ep.out_fmt == 1) {   // "f16" activation format: one fp16 plane (8-byte stores)
+        const long long o = (((long long)b * oh + oy) * ow + ox) * ch + cbase;
+        uint2 ph;
+        ph.x = pack_f16x2_sat(v0 * sn.x, v1 * sn.y);
+        ph.y = pack_f16x2_sat(v2 * sn.z, v3 * sn.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out_hi) + o) = ph;
+      } else if (hi) {
         v0 *= sn.x; v1 *= sn.y; v2 *= sn.z; v3 *= sn.w;
         const __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
         const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
@@ -285,7 +297,9 @@ extern "C" int maua_blur_act_nhwc(const float* u, const float* k4, const MauaCon
   using namespace maua;
   MAUA_CHECK_ARG(u && k4 && ep_host && batch >= 0 && ch >= 4 && hu >= 2 && wu >= 2, "blur_act_nhwc: bad arguments");
   MAUA_CHECK_ARG(ch % 4 == 0, "blur_act_nhwc: channels must be a multiple of 4");
-  MAUA_CHECK_ARG((ep_host->out_hi != nullptr) == (ep_host->out_lo != nullptr), "blur_act_nhwc: hi/lo must come in pairs");
+  MAUA_CHECK_ARG(ep_host->out_fmt == 0 || ep_host->out_fmt == 1, "blur_act_nhwc: out_fmt must be 0 or 1");
+  MAUA_CHECK_ARG(ep_host->out_fmt == 1 || (ep_host->out_hi != nullptr) == (ep_host->out_lo != nullptr),
+                 "blur_act_nhwc: hi/lo must come in pairs");
   MAUA_CHECK_ARG(!ep_host->noise || ep_host->noise_weight, "blur_act_nhwc: noise without weight");
   if (batch == 0) return MAUA_OK;
   MAUA_CHECK_ARG(batch <= 65535, "blur_act_nhwc: batch too large");

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -64,6 +65,23 @@ __host__ __device__ __forceinline__ int floor_div(int a, int b) {
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// fp32 pair -> packed fp16x2 (low half = a), round-to-nearest, SATURATING to +-65504 instead of overflowing to inf:
+// the "f16" activation format of the tensor-core path must stay finite whatever a checkpoint's dynamic range is.
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(a), "f"(b));  // d = {hi: first source, lo: second}
+  return r;
+}
+__device__ __forceinline__ __half f16_sat(float a) {
+  const uint32_t r = pack_f16x2_sat(a, 0.f);
+  return __ushort_as_half((unsigned short)(r & 0xFFFFu));
+}
+// fp32 -> (hi, lo) fp16 pair with hi + lo == x up to 2^-22 relative (weights of the "f16" path)
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = f16_sat(x);
+  lo = f16_sat(x - __half2float(hi));
 }
 
 // Packed dual fp32 FMA (sm_100 `fma.rn.f32x2`): two IEEE-rounded FMAs per issue slot; each lane rounds exactly like

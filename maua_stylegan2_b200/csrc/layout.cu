@@ -10,8 +10,10 @@
 
 namespace maua {
 
-__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
-                                                          __nv_bfloat16* __restrict__ lo, int cout, int cin, int kk,
+// F16 = false: bf16 (hi, lo);  F16 = true: fp16 (hi, lo)
+template <bool F16>
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi,
+                                                          uint16_t* __restrict__ lo, int cout, int cin, int kk,
                                                           float scale, long long total) {
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int ci = (int)(i % cin);
@@ -19,15 +21,26 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
     const int co = (int)(r % cout);
     const int t = (int)(r / cout);
     const float v = __ldg(w + ((long long)co * cin + ci) * kk + t) * scale;
-    split_bf16(v, hi[i], lo[i]);
+    if (F16) {
+      __half h, l;
+      split_f16(v, h, l);
+      hi[i] = __half_as_ushort(h);
+      lo[i] = __half_as_ushort(l);
+    } else {
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      hi[i] = __bfloat16_as_ushort(h);
+      lo[i] = __bfloat16_as_ushort(l);
+    }
   }
 }
 
 // grid (ceil(HW/32), ceil(C/32), B), block (32, 8): 32x32 (pixel, channel) transpose through shared memory.
+// lo == nullptr: single fp16 plane (the "f16" activation format); otherwise the bf16 (hi, lo) pair
 __global__ void __launch_bounds__(256) modulate_split_kernel(const float* __restrict__ x, long long x_bstride,
                                                              const float* __restrict__ s,
-                                                             __nv_bfloat16* __restrict__ hi,
-                                                             __nv_bfloat16* __restrict__ lo, int ch, long long hw) {
+                                                             uint16_t* __restrict__ hi,
+                                                             uint16_t* __restrict__ lo, int ch, long long hw) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -51,7 +64,14 @@ __global__ void __launch_bounds__(256) modulate_split_kernel(const float* __rest
     const int c = c0 + threadIdx.x;
     if (c < ch && p < hw) {
       const long long o = ((long long)b * hw + p) * ch + c;
-      split_bf16(tile[threadIdx.x][j], hi[o], lo[o]);
+      if (lo == nullptr) {
+        hi[o] = __half_as_ushort(f16_sat(tile[threadIdx.x][j]));
+      } else {
+        __nv_bfloat16 h, l;
+        split_bf16(tile[threadIdx.x][j], h, l);
+        hi[o] = __bfloat16_as_ushort(h);
+        lo[o] = __bfloat16_as_ushort(l);
+      }
     }
   }
 }
@@ -65,10 +85,22 @@ extern "C" int maua_pack_weight_bf16x2(const float* w, void* w_hi, void* w_lo, i
   const long long total = (long long)ksize * ksize * cout * cin;
   long long blocks = ceil_div(total, 256LL);
   if (blocks > 148LL * 16) blocks = 148LL * 16;
-  pack_weight_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(w_hi), reinterpret_cast<__nv_bfloat16*>(w_lo), cout, cin, ksize * ksize,
-      w_scale, total);
+  pack_weight_kernel<false><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      w, reinterpret_cast<uint16_t*>(w_hi), reinterpret_cast<uint16_t*>(w_lo), cout, cin, ksize * ksize, w_scale, total);
   MAUA_CHECK_LAUNCH("pack_weight");
+  return MAUA_OK;
+}
+
+extern "C" int maua_pack_weight_f16x2(const float* w, void* w_hi, void* w_lo, int cout, int cin, int ksize,
+                                      float w_scale, void* stream) {
+  using namespace maua;
+  MAUA_CHECK_ARG(w && w_hi && w_lo && cout >= 1 && cin >= 1 && ksize >= 1, "pack_weight_f16x2: bad arguments");
+  const long long total = (long long)ksize * ksize * cout * cin;
+  long long blocks = ceil_div(total, 256LL);
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  pack_weight_kernel<true><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      w, reinterpret_cast<uint16_t*>(w_hi), reinterpret_cast<uint16_t*>(w_lo), cout, cin, ksize * ksize, w_scale, total);
+  MAUA_CHECK_LAUNCH("pack_weight_f16x2");
   return MAUA_OK;
 }
 
@@ -81,7 +113,21 @@ extern "C" int maua_modulate_split_nhwc(const float* x, long long x_bstride, con
   const long long hw = (long long)h * w;
   dim3 grid((unsigned)ceil_div(hw, 32LL), ceil_div(ch, 32), batch);
   modulate_split_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(
-      x, x_bstride, s, reinterpret_cast<__nv_bfloat16*>(x_hi), reinterpret_cast<__nv_bfloat16*>(x_lo), ch, hw);
+      x, x_bstride, s, reinterpret_cast<uint16_t*>(x_hi), reinterpret_cast<uint16_t*>(x_lo), ch, hw);
   MAUA_CHECK_LAUNCH("modulate_split");
+  return MAUA_OK;
+}
+
+extern "C" int maua_modulate_f16_nhwc(const float* x, long long x_bstride, const float* s, void* x_f16, int batch, int ch,
+                                      int h, int w, void* stream) {
+  using namespace maua;
+  MAUA_CHECK_ARG(x && x_f16 && batch >= 0 && ch >= 1 && h >= 1 && w >= 1, "modulate_f16: bad arguments");
+  if (batch == 0) return MAUA_OK;
+  MAUA_CHECK_ARG(batch <= 65535 && ch <= 65535 * 32, "modulate_f16: shape too large");
+  const long long hw = (long long)h * w;
+  dim3 grid((unsigned)ceil_div(hw, 32LL), ceil_div(ch, 32), batch);
+  modulate_split_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(x, x_bstride, s, reinterpret_cast<uint16_t*>(x_f16),
+                                                                     nullptr, ch, hw);
+  MAUA_CHECK_LAUNCH("modulate_f16");
   return MAUA_OK;
 }

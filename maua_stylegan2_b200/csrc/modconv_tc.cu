@@ -369,8 +369,9 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
   using namespace maua;
   using namespace maua::tc;
   MAUA_CHECK_ARG(x_hi && w_hi && ep_host, "modconv_tc: null pointer");
-  MAUA_CHECK_ARG(n_products == 1 || n_products == 3, "modconv_tc: n_products must be 1 or 3");
-  MAUA_CHECK_ARG(n_products == 1 || (x_lo && w_lo), "modconv_tc: lo planes required for n_products == 3");
+  MAUA_CHECK_ARG(n_products >= 1 && n_products <= 3, "modconv_tc: n_products must be 1, 2 (fp16) or 3");
+  MAUA_CHECK_ARG(n_products != 3 || (x_lo && w_lo), "modconv_tc: lo planes required for n_products == 3");
+  MAUA_CHECK_ARG(n_products != 2 || w_lo, "modconv_tc: the fp16 mode needs the fp16 (hi, lo) weight pair");
   MAUA_CHECK_ARG(batch >= 0 && h >= 1 && w >= 1, "modconv_tc: bad shape");
   MAUA_CHECK_ARG(cin % 32 == 0 && cin >= 32, "modconv_tc: Cin must be a multiple of 32");
   MAUA_CHECK_ARG(cout % 16 == 0 && cout >= 16, "modconv_tc: Cout must be a multiple of 16");
@@ -380,7 +381,9 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
   } else {
     MAUA_CHECK_ARG(ep.out_f32_nchw || ep.out_hi || ep.rgb_out, "modconv_tc: no output requested");
     MAUA_CHECK_ARG((ep.rgb_out != nullptr) == (ep.rgb_w != nullptr), "modconv_tc: rgb_w / rgb_out must come in pairs");
-    MAUA_CHECK_ARG((ep.out_hi != nullptr) == (ep.out_lo != nullptr), "modconv_tc: hi/lo outputs must come in pairs");
+    MAUA_CHECK_ARG(ep.out_fmt == 0 || ep.out_fmt == 1, "modconv_tc: out_fmt must be 0 (bf16 pair) or 1 (fp16 plane)");
+    MAUA_CHECK_ARG(ep.out_fmt == 1 || (ep.out_hi != nullptr) == (ep.out_lo != nullptr),
+                   "modconv_tc: hi/lo outputs must come in pairs");
     MAUA_CHECK_ARG(!ep.noise || ep.noise_weight, "modconv_tc: noise without noise_weight");
   }
   if (batch == 0) return MAUA_OK;
@@ -394,6 +397,8 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
   }
 
   MAUA_CHECK_ARG(!ep.rgb_out, "modconv_tc: fused ToRGB is not available for this shape (needs Cout <= 128, H,W >= 64)");
+  MAUA_CHECK_ARG(n_products != 2 && ep.out_fmt == 0,
+                 "modconv_tc: the fp16 activation format is only implemented by the halo kernel (GEMM grid >= 64 x 32)");
   Params p;
   p.B = batch; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout;
   p.GH = up ? h + 1 : h;

@@ -38,8 +38,9 @@ struct Params {
   int BN, n_tiles;
   int n_kchunks;
   int SA, SB;
-  int nprod;
-  int cat;               // 1: hi*[hi|lo] as ONE MMA of N = 2*BN plus lo*hi (2 MMAs per K-step instead of 3)
+  int a_planes;          // activation planes per A stage: 2 = bf16 (hi, lo) pair; 1 = single plane (bf16 fast mode / fp16)
+  int b_planes;          // weight planes per B stage: 2 = (hi, lo) pair, 1 = hi only
+  int cat;               // 1: [w_hi | w_lo] consumed as ONE MMA of N = 2*BN (accumulator halves added by the epilogue)
   uint32_t a_plane;      // bytes of one bf16 plane of the halo, rounded up to 1024
   uint32_t tmem_cols;
   int AS;                // TMEM accumulator stages (2 = epilogue of item i overlaps the MMAs of item i+1)
@@ -72,8 +73,13 @@ __constant__ TapList c_taps[8] = {
 
 __device__ __forceinline__ float lrelu_s(float v, float slope, float scale) { return (v > 0.f ? v : v * slope) * scale; }
 
-// MODE: 0 = one product (hi*hi), 1 = three products as three N = BN MMAs, 2 = "concat": hi*[hi|lo] as one N = 2*BN MMA
-// plus lo*hi.  A template parameter (not p.nprod / p.cat) so that the issue loop is branch-free.
+// MODE (bf16 operands): 0 = one product (hi*hi), 1 = three products as three N = BN MMAs, 2 = "concat": hi*[hi|lo] as
+//   one N = 2*BN MMA plus lo*hi.
+// MODE (fp16 operands, "f16" activation format: ONE fp16 activation plane, weights as an fp16 (hi, lo) pair, so the
+//   weight operand is exact to 2^-22 and the only rounding is the 11-bit activation): 3 = a*w_hi + a*w_lo as two
+//   N = BN MMAs into the same accumulator, 4 = a*[w_hi|w_lo] as ONE N = 2*BN MMA (BN <= 64: small-N MMAs are bound by the
+//   4 KB A-operand fetch, so halving the A planes AND the MMA count nearly halves the tensor-pipe time of those layers).
+// A template parameter (not p.cat / p.a_planes) so that the issue loop is branch-free.
 template <int KC, bool UP, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -84,7 +90,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   static_assert(KC == 32, "the issue loop below is written for two K=16 steps per chunk");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_stage = 2 * p.a_plane;
+  const uint32_t a_stage = (uint32_t)p.a_planes * p.a_plane;
   const uint32_t b_half = (uint32_t)p.BN * ROW, b_stage = 2 * b_half;
   const uint32_t a_base = smem0;
   const uint32_t b_base = a_base + (uint32_t)p.SA * a_stage;
@@ -102,10 +108,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi);
     prefetch_tmap(&tm_b_hi);
-    if (p.nprod > 1) {
-      prefetch_tmap(&tm_a_lo);
-      prefetch_tmap(&tm_b_lo);
-    }
+    if (p.a_planes > 1) prefetch_tmap(&tm_a_lo);
+    if (p.b_planes > 1) prefetch_tmap(&tm_b_lo);
     for (int i = 0; i < p.SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
     for (int i = 0; i < p.AS; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4 * EPI_GROUPS); }
@@ -155,20 +159,20 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if ((p.dbg & 2) && item != (int)blockIdx.x) {
           mbar_arrive(a_full + 8 * ia);
         } else {
-        mbar_expect_tx(a_full + 8 * ia, halo_bytes * (p.nprod > 1 ? 2 : 1));
+        mbar_expect_tx(a_full + 8 * ia, halo_bytes * (uint32_t)p.a_planes);
         const uint32_t dst = a_base + ia * a_stage;
         tma_load_4d(dst, &tm_a_hi, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
-        if (p.nprod > 1) tma_load_4d(dst + p.a_plane, &tm_a_lo, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
+        if (p.a_planes > 1) tma_load_4d(dst + p.a_plane, &tm_a_lo, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
         }
         if (++ia == p.SA) { ia = 0; pa ^= 1; }
 #pragma unroll 1
         for (int t = 0; t < tl.n; ++t) {
           if (p.resident_b && item != (int)blockIdx.x) break;  // weights already resident in shared memory
           mbar_wait(b_empty + 8 * ib, pb ^ 1);
-          mbar_expect_tx(b_full + 8 * ib, p.nprod > 1 ? b_stage : b_half);
+          mbar_expect_tx(b_full + 8 * ib, p.b_planes > 1 ? b_stage : b_half);
           const uint32_t dstb = b_base + ib * b_stage;
           tma_load_3d(dstb, &tm_b_hi, b_full + 8 * ib, c0, n0, tl.t[t].tap);
-          if (p.nprod > 1) tma_load_3d(dstb + b_half, &tm_b_lo, b_full + 8 * ib, c0, n0, tl.t[t].tap);
+          if (p.b_planes > 1) tma_load_3d(dstb + b_half, &tm_b_lo, b_full + 8 * ib, c0, n0, tl.t[t].tap);
           if (++ib == p.SB) { ib = 0; pb ^= 1; }
         }
       }
@@ -179,8 +183,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const bool leader = elect_one_sync();
     // The issue loop must stay far below the ~50 cycles a 128x32x16 MMA occupies the tensor pipe: all descriptor
     // fields are folded into per-stage base values up front; per MMA only 64-bit adds of small constants remain.
-    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN);
-    const uint32_t idesc2 = make_idesc_bf16(128, (uint32_t)(2 * p.BN));
+    const uint32_t idesc = MODE >= 3 ? make_idesc_f16(128, (uint32_t)p.BN) : make_idesc_bf16(128, (uint32_t)p.BN);
+    const uint32_t idesc2 = MODE >= 3 ? make_idesc_f16(128, (uint32_t)(2 * p.BN)) : make_idesc_bf16(128, (uint32_t)(2 * p.BN));
     const uint64_t sbo_field = (uint64_t)((((uint32_t)p.HW_ * ROW) >> 4) & 0x3FFF) << 32;
     const uint64_t da0 = (make_kmajor_desc(a_base, ROW) & ~(0x3FFFull << 32)) | sbo_field;  // A stage 0, hi plane
     const uint64_t db0 = make_kmajor_desc(b_base, ROW);                                      // B stage 0, hi plane
@@ -227,6 +231,14 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                   umma_bf16(acc, dah + 2, dbh + 2, idesc2, 1u);
                   umma_bf16(acc, dal, dbh, idesc, 1u);
                   umma_bf16(acc, dal + 2, dbh + 2, idesc, 1u);
+                } else if (mode == 4) {  // fp16: a * [w_hi | w_lo], one N = 2*BN MMA per K-step
+                  umma_bf16(acc, dah, dbh, idesc2, first);
+                  umma_bf16(acc, dah + 2, dbh + 2, idesc2, 1u);
+                } else if (mode == 3) {  // fp16: a * w_hi + a * w_lo into the same accumulator
+                  umma_bf16(acc, dah, dbh, idesc, first);
+                  umma_bf16(acc, dah + 2, dbh + 2, idesc, 1u);
+                  umma_bf16(acc, dah, dbl, idesc, 1u);
+                  umma_bf16(acc, dah + 2, dbl + 2, idesc, 1u);
                 } else {
                   umma_bf16(acc, dah, dbh, idesc, first);
                   umma_bf16(acc, dah + 2, dbh + 2, idesc, 1u);
@@ -434,7 +446,20 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 dst[(2 * i + 1) * plane] = v[i].y;
               }
             }
-            if (ep.out_hi) {
+            if (ep.out_hi && ep.out_fmt == 1) {
+              // "f16" activation format for the consumer: ONE fp16 plane of o * s_next (saturating conversion)
+              uint32_t h[8];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 sv = sptr[(c >> 2) + q];
+                const float2 a01 = fmul2(v[2 * q], make_float2(sv.x, sv.y)), a23 = fmul2(v[2 * q + 1], make_float2(sv.z, sv.w));
+                h[2 * q] = pack_f16x2_sat(a01.x, a01.y);
+                h[2 * q + 1] = pack_f16x2_sat(a23.x, a23.y);
+              }
+              uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(ep.out_hi) + pix * Cout + n0 + c);
+              dh[0] = make_uint4(h[0], h[1], h[2], h[3]);
+              dh[1] = make_uint4(h[4], h[5], h[6], h[7]);
+            } else if (ep.out_hi) {
               uint32_t h[8], l[8];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -528,6 +553,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   // The search below (cost model) only decides when the preferred configuration is infeasible or leaves most SMs idle.
   int best_r = 0, best_bn = 0, best_cat = 0, best_groups = 1;
   static const int force_groups = [] { const char* e = getenv("MAUA_TC_GROUPS"); return e ? atoi(e) : 0; }();
+  const uint32_t a_planes = n_products == 3 ? 2u : 1u;   // n_products: 1 = bf16 hi*hi, 3 = bf16 split, 2 = fp16 (a * (w_hi + w_lo))
   auto n_ctas = [&](int r, int bn, int groups) {
     return tiles_x * ceil_div(rows16, (long long)r) * batch * (cout / bn) * groups;
   };
@@ -540,7 +566,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     if (r * blk * (nphase / groups) > tmem_cap) return false;
     const uint32_t plane = align1k((uint32_t)((TH * r + (up ? 1 : 2)) * (up ? TW + 1 : TW + 2) * kc * 2));
     const uint32_t b_st = 2u * bn * kc * 2u;
-    return 2 * plane + 4 * b_st <= budget;  // A halo (hi+lo) + a B ring deep enough to hide TMA latency
+    return a_planes * plane + 4 * b_st <= budget;  // A halo (hi[+lo]) + a B ring deep enough to hide TMA latency
   };
   auto search = [&]() {
     double best_cost = 1e30;
@@ -558,7 +584,8 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
             // ~115 B/clk); a single accumulator stage exposes the epilogue (penalty); L2->SMEM bytes per cycle as a
             // secondary term (the halo is re-loaded once per phase group)
             auto mma_cycles = [](double n) { const double f = (4096.0 + 32.0 * n) / 115.0; return n / 2.0 > f ? n / 2.0 : f; };
-            const double per_kstep = cat ? mma_cycles(2.0 * bn) + mma_cycles(bn) : (n_products > 1 ? 3.0 : 1.0) * mma_cycles(bn);
+            const double per_kstep = n_products == 2 ? (cat ? mma_cycles(2.0 * bn) : 2.0 * mma_cycles(bn))
+                                     : cat ? mma_cycles(2.0 * bn) + mma_cycles(bn) : (n_products > 1 ? 3.0 : 1.0) * mma_cycles(bn);
             const double traffic = (groups * (TH * r + 2) * 10.0 / 9.0 + bn) / ((double)r * bn);
             const double cost = per_kstep / bn * (2 * r * blk * nph_item <= 512 ? 1.0 : 1.2) + 0.15 * traffic;
             const bool enough = ctas >= 120, best_enough = best_ctas >= 120;
@@ -576,6 +603,10 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     else if (cout == 128) { pr = up ? 1 : 2; pbn = 128; pg = up ? 2 : 1; }
     else if (cout == 64) { pr = up ? 2 : 1; pbn = 64; pg = up ? 2 : 1; pcat = up ? 0 : 1; }
     else { pr = up ? 1 : 4; pbn = cout; pcat = 1; }
+    if (n_products == 2 && cout <= 64) {  // fp16: the concat MMA is the whole product -> always for BN <= 64
+      pcat = 1;
+      if (cout == 64) { pr = up ? 1 : 2; pg = up ? 2 : 1; }
+    }
     if (force_groups && up) pg = force_groups;
     while (pr > 1 && pr > rows16) pr >>= 1;
     // keep (most of) the 148 SMs busy: first fewer stacked tiles, then more phase groups, then narrower N
@@ -600,14 +631,15 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   p.tiles_x = (int)tiles_x;
   p.tiles_y = (int)ceil_div(rows16, (long long)R);
   p.n_kchunks = n_kchunks;
-  p.nprod = n_products;
+  p.a_planes = (int)a_planes;
+  p.b_planes = n_products == 1 ? 1 : 2;
   p.a_plane = align1k((uint32_t)(p.HW_ * p.HH_ * kc * 2));
   p.cat = best_cat;
   const int blk_cols = p.cat ? 2 * bn : bn;
   p.n_groups = best_groups;
   p.n_phase = nphase / best_groups;
   int cols = 32;
-  const uint32_t a_stage = 2 * p.a_plane, b_stage = 2u * bn * kc * 2u;
+  const uint32_t a_stage = a_planes * p.a_plane, b_stage = 2u * bn * kc * 2u;
   p.SA = (2 * a_stage + 4 * b_stage <= budget) ? 2 : 1;
   int sb = (int)((budget - (uint32_t)p.SA * a_stage) / b_stage);
   // small layers: keep ALL weight tiles of the layer in shared memory for the lifetime of the persistent CTA
@@ -635,8 +667,8 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     fprintf(stderr, "[modconv_tc2] %s B%d %d->%d @%dx%d: R=%d BN=%d cat=%d groups=%d resB=%d AS=%d SA=%d SB=%d smem=%zuKB tmem=%u items=%lld grid=%lld\n",
             up ? "up" : "same", batch, cin, cout, h, w, R, bn, p.cat, p.n_groups, p.resident_b, p.AS, p.SA, p.SB, smem / 1024, p.tmem_cols, items, grid);
 
-  set_conv_config("v2 up=%d R=%d BN=%d cat=%d groups=%d resB=%d AS=%d SA=%d SB=%d items=%lld grid=%lld", up, R, bn, p.cat,
-                  p.n_groups, p.resident_b, p.AS, p.SA, p.SB, items, grid);
+  set_conv_config("v2 up=%d R=%d BN=%d cat=%d groups=%d prod=%d resB=%d AS=%d SA=%d SB=%d items=%lld grid=%lld", up, R, bn, p.cat,
+                  p.n_groups, n_products, p.resident_b, p.AS, p.SA, p.SB, items, grid);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   const auto swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const cuuint64_t adims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
@@ -646,13 +678,17 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   const cuuint64_t bstr[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
   const cuuint32_t bbox[3] = {(cuuint32_t)kc, (cuuint32_t)bn, 1};
   int rc;
-  if ((rc = tmap::encode(&ta_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x_hi, 4, adims, astr, abox, swz))) return rc;
-  if ((rc = tmap::encode(&tb_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_hi, 3, bdims, bstr, bbox, swz))) return rc;
-  if (n_products > 1) {
-    if ((rc = tmap::encode(&ta_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x_lo, 4, adims, astr, abox, swz))) return rc;
-    if ((rc = tmap::encode(&tb_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_lo, 3, bdims, bstr, bbox, swz))) return rc;
+  const auto dt = n_products == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  if ((rc = tmap::encode(&ta_hi, dt, x_hi, 4, adims, astr, abox, swz))) return rc;
+  if ((rc = tmap::encode(&tb_hi, dt, w_hi, 3, bdims, bstr, bbox, swz))) return rc;
+  if (a_planes > 1) {
+    if ((rc = tmap::encode(&ta_lo, dt, x_lo, 4, adims, astr, abox, swz))) return rc;
   } else {
     ta_lo = ta_hi;
+  }
+  if (p.b_planes > 1) {
+    if ((rc = tmap::encode(&tb_lo, dt, w_lo, 3, bdims, bstr, bbox, swz))) return rc;
+  } else {
     tb_lo = tb_hi;
   }
 #define MAUA_TC2_LAUNCH(KCV, UPV, MODEV)                                                                            \
@@ -660,12 +696,17 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(modconv_tc2_kernel<KCV, UPV, MODEV>), smem));    \
     modconv_tc2_kernel<KCV, UPV, MODEV><<<(unsigned)grid, THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep);      \
   } while (0)
-  const int mode = n_products == 1 ? 0 : (p.cat ? 2 : 1);
-  if (up) {
-    if (mode == 0) MAUA_TC2_LAUNCH(32, true, 0); else if (mode == 1) MAUA_TC2_LAUNCH(32, true, 1); else MAUA_TC2_LAUNCH(32, true, 2);
-  } else {
-    if (mode == 0) MAUA_TC2_LAUNCH(32, false, 0); else if (mode == 1) MAUA_TC2_LAUNCH(32, false, 1); else MAUA_TC2_LAUNCH(32, false, 2);
+  const int mode = n_products == 1 ? 0 : (n_products == 2 ? (p.cat ? 4 : 3) : (p.cat ? 2 : 1));
+#define MAUA_TC2_MODES(UPV)                                                   \
+  switch (mode) {                                                             \
+    case 0: MAUA_TC2_LAUNCH(32, UPV, 0); break;                               \
+    case 1: MAUA_TC2_LAUNCH(32, UPV, 1); break;                               \
+    case 2: MAUA_TC2_LAUNCH(32, UPV, 2); break;                               \
+    case 3: MAUA_TC2_LAUNCH(32, UPV, 3); break;                               \
+    default: MAUA_TC2_LAUNCH(32, UPV, 4); break;                              \
   }
+  if (up) { MAUA_TC2_MODES(true) } else { MAUA_TC2_MODES(false) }
+#undef MAUA_TC2_MODES
 #undef MAUA_TC2_LAUNCH
   MAUA_CHECK_LAUNCH("modconv_tc(v2)");
   return MAUA_OK;

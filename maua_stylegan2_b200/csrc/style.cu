@@ -86,6 +86,32 @@ __global__ void __launch_bounds__(256) style_d_kernel(const MauaStyleJob* __rest
     ss[i] = v * v;
   }
   __syncthreads();
+  // Optional power-of-two range normalisation (s_norm_out): every block of the job holds the complete s^2 rows, so each
+  // derives the per-sample exponent itself (no cross-block reduction); block row 0 writes the normalised styles.
+  __shared__ int s_exp[SB];
+  if (tid < SB) s_exp[tid] = 0;
+  if (job.s_norm_out != nullptr) {   // (uniform over the block)
+    __syncthreads();
+    if (warp < SB) {
+      float m = 0.f;
+      for (int k = lane; k < job.cin; k += 32) m = fmaxf(m, ss[warp * job.cin + k]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      int e = 0;
+      if (m > 0.f) frexpf(sqrtf(m) * 1.0000002f, &e);   // max|s| = f * 2^e, f in [0.5, 1)  ->  |s| * 2^-e < 1
+      if (lane == 0) s_exp[warp] = e;
+    }
+    __syncthreads();
+    if (blockIdx.y == 0) {
+      for (int i = tid; i < nb * job.cin; i += 256) {
+        const int bl = i / job.cin, k = i - bl * job.cin;
+        const long long o = (long long)(b0 + bl) * job.cin + k;
+        job.s_norm_out[o] = ldexpf(job.s_out[o], -s_exp[bl]);
+      }
+    }
+  } else {
+    __syncthreads();
+  }
   for (int r = row0 + warp; r < min(row0 + SROWS, job.cout); r += 8) {
     const float* wr = job.wsq + (long long)r * job.cin;
     float acc[SB];
@@ -102,7 +128,7 @@ __global__ void __launch_bounds__(256) style_d_kernel(const MauaStyleJob* __rest
       float a = acc[0];
 #pragma unroll
       for (int j = 1; j < SB; ++j) a = (lane == j) ? acc[j] : a;
-      job.d_out[(long long)(b0 + lane) * job.cout + r] = rsqrtf(a + 1e-8f);
+      job.d_out[(long long)(b0 + lane) * job.cout + r] = ldexpf(rsqrtf(a + 1e-8f), s_exp[lane]);
     }
   }
 }

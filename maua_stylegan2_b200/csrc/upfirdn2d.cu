@@ -140,6 +140,126 @@ __global__ void __launch_bounds__(256, MINB) blur_tile_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Software-pipelined persistent variant of blur_tile_kernel: a CTA walks tiles with stride gridDim.x and keeps the
+// global loads of tile i+1 IN FLIGHT (registers) while it computes tile i out of shared memory.  The one-shot kernel
+// alternates load / compute / store phases per CTA, so only a fraction of the resident CTAs have requests outstanding
+// at any time (ncu: DRAM 55 %, 0.69 of HBM peak, latency-bound); here every CTA always has ~18 KB outstanding.
+// TMA cannot stage these planes: their row pitch (2H+1 floats) is not a multiple of 16 bytes.
+// Same tile shape, same FMA order (y-major, x-minor) -> bit-identical results.
+// ---------------------------------------------------------------------------------------------------------------
+template <int TW, int RY, int MINB>
+__global__ void __launch_bounds__(256, MINB) blur_tile_pipe_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                             const float* __restrict__ k, UfdParams p, int vec_store,
+                                                             long long n_tiles) {
+  constexpr int TXN = TW / 4;
+  constexpr int TYN = 256 / TXN;
+  constexpr int TH = TYN * RY;
+  constexpr int COLS = TW + 4;
+  constexpr int PITCH = TW + 8;
+  constexpr int ROWS = TH + 3;
+  constexpr int RPW = (ROWS + 7) / 8;
+  constexpr int CPL = (COLS + 31) / 32;
+  __shared__ __align__(16) float sx[ROWS * PITCH];
+  __shared__ float skf[16];
+
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int tiles_x = (p.out_w + TW - 1) / TW;
+  const int tiles_y = (p.out_h + TH - 1) / TH;
+  const long long per_plane = (long long)tiles_x * tiles_y;
+  if (tid < 16) {
+    const int ky = tid >> 2, kx = tid & 3;
+    float v = 0.f;
+    if (ky < p.kh && kx < p.kw) v = k[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)];
+    skf[tid] = v;
+  }
+  __syncthreads();
+  float kf[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kf[i] = skf[i];
+
+  float v[RPW][CPL];
+  auto load_tile = [&](long long t) {
+    const long long plane = t / per_plane;
+    const int rem = (int)(t - plane * per_plane);
+    const int ix0 = (rem % tiles_x) * TW - p.px0, iy0 = (rem / tiles_x) * TH - p.py0;
+    const float* xp = x + plane * (long long)p.in_h * p.in_w;
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int r = wrp + 8 * i;
+      const int iy = iy0 + r;
+      const bool row_ok = (r < ROWS) && (iy >= 0) && (iy < p.in_h);
+      const float* src = xp + (long long)iy * p.in_w + ix0;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int c = lane + 32 * j;
+        const int ix = ix0 + c;
+        v[i][j] = (row_ok && c < COLS && ix >= 0 && ix < p.in_w) ? __ldg(src + c) : 0.f;
+      }
+    }
+  };
+
+  long long t = blockIdx.x;
+  if (t < n_tiles) load_tile(t);
+  const int tx = tid % TXN, ty = tid / TXN;
+  for (; t < n_tiles; t += gridDim.x) {
+    __syncthreads();  // the previous tile's readers are done with sx
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int r = wrp + 8 * i;
+      if (r < ROWS) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const int c = lane + 32 * j;
+          if (c < COLS) sx[r * PITCH + c] = v[i][j];
+        }
+      }
+    }
+    __syncthreads();
+    const long long tn = t + gridDim.x;
+    if (tn < n_tiles) load_tile(tn);   // in flight during the FMA / store phase below
+
+    float acc[RY][4];
+#pragma unroll
+    for (int j = 0; j < RY; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < RY + 3; ++r) {
+      const float4 a = *reinterpret_cast<const float4*>(&sx[(ty * RY + r) * PITCH + tx * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sx[(ty * RY + r) * PITCH + tx * 4 + 4]);
+      const float row[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < RY; ++j) {
+        const int ky = r - j;
+        if (ky >= 0 && ky < 4) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) acc[j][i] = __fmaf_rn(row[i + kx], kf[ky * 4 + kx], acc[j][i]);
+        }
+      }
+    }
+    const long long plane = t / per_plane;
+    const int rem = (int)(t - plane * per_plane);
+    const int ox = (rem % tiles_x) * TW + tx * 4, oy0 = (rem / tiles_x) * TH;
+    float* yp = y + plane * (long long)p.out_h * p.out_w;
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      const int oy = oy0 + ty * RY + j;
+      if (oy >= p.out_h) continue;
+      float* dst = yp + (long long)oy * p.out_w + ox;
+      if (vec_store && ox + 3 < p.out_w) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (ox + i < p.out_w) dst[i] = acc[j][i];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // generic kernel: one thread per output element (ox fastest, then minor? no: minor fastest as in memory)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) generic_kernel(const float* __restrict__ x, float* __restrict__ y,
@@ -194,14 +314,25 @@ extern "C" int maua_upfirdn2d_f32(const float* x, float* y, const float* k, int 
   if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && kh <= 4 && kw <= 4 && minor == 1) {
     const int vec = ((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (p.out_w & 3) == 0) ? 1 : 0;
     const int planes_y = major < 32768 ? major : 32768;
-    static const int variant = [] { const char* e = getenv("MAUA_UFD_VARIANT"); return e ? atoi(e) : 0; }();
+    const char* ve = getenv("MAUA_UFD_VARIANT");   // read per call (tests / tuning flip it)
+    const int variant = ve ? atoi(ve) : 0;
 #define MAUA_BLUR_LAUNCH(TWV, RYV, MINBV)                                                    \
   do {                                                                                       \
     constexpr int TH = (256 / (TWV / 4)) * RYV;                                              \
     dim3 grid(ceil_div(p.out_w, TWV) * ceil_div(p.out_h, TH), planes_y);                     \
     blur_tile_kernel<TWV, RYV, MINBV><<<grid, 256, 0, st>>>(x, y, k, p, vec);                \
   } while (0)
-    if (p.out_w > 64) {
+    if (p.out_w > 64 && variant >= 3) {
+      // software-pipelined persistent kernel (variant 3: 3 CTAs/SM, 4: 4 CTAs/SM, 5: 2 CTAs/SM)
+      constexpr int TH = (256 / (128 / 4)) * 4;
+      const long long n_tiles = (long long)ceil_div(p.out_w, 128) * ceil_div(p.out_h, TH) * major;
+      const int per_sm = variant == 4 ? 4 : (variant == 5 ? 2 : 3);
+      long long g = (long long)device_sm_count() * per_sm;
+      if (g > n_tiles) g = n_tiles;
+      if (variant == 4) blur_tile_pipe_kernel<128, 4, 4><<<(unsigned)g, 256, 0, st>>>(x, y, k, p, vec, n_tiles);
+      else if (variant == 5) blur_tile_pipe_kernel<128, 4, 2><<<(unsigned)g, 256, 0, st>>>(x, y, k, p, vec, n_tiles);
+      else blur_tile_pipe_kernel<128, 4, 3><<<(unsigned)g, 256, 0, st>>>(x, y, k, p, vec, n_tiles);
+    } else if (p.out_w > 64) {
       // measured on B200, [4,32,2049,2049]: (128,4) tiles at 5 CTAs/SM 4.60 TB/s | 4 CTAs 4.24 | (128,8)x2 3.43 |
       // (64,4)x4 3.92 | (128,2)x6 3.93   (MAUA_UFD_VARIANT keeps the alternatives reachable for re-tuning)
       if (variant == 1) MAUA_BLUR_LAUNCH(128, 4, 4);

@@ -110,6 +110,17 @@ def generate(ckpt, audio_file, initialize=None, get_latents=None, get_noise=None
              channel_multiplier=2, randomize_noise=False, ffmpeg_preset="slow", base_res_factor=1, output_file=None,
              args=None, audio=None, sink=None, generator=None, latent_selection=None):
     started = time.time()
+    # Multi-GPU (the reference's `--dataparallel`, generate_audiovisual.py:54-55,249, is single-process nn.DataParallel):
+    # here one process per GPU under torchrun; every rank runs generate(), frames are sharded by render.render and only
+    # rank 0 writes the video.  `dataparallel=True` without torchrun has a single rank and renders on one GPU.
+    from . import parallel
+
+    rank, world, local_rank = parallel.init_from_env()
+    if world > 1:
+        th.cuda.set_device(local_rank)
+    elif dataparallel and th.cuda.device_count() > 1:
+        print("--dataparallel: launch with `torchrun --nproc-per-node N -m maua_stylegan2_b200.generate_audiovisual ...` "
+              "to shard the frames over N GPUs; this process renders on one GPU.")
     if args is None:
         args = _namespace(dict(locals()), skip=("audio", "sink", "generator", "latent_selection", "started"))
     ar.set_SMF(fps / 30)  # smoothing independent of the frame rate (:101)
@@ -146,7 +157,7 @@ def generate(ckpt, audio_file, initialize=None, get_latents=None, get_noise=None
                                    dataparallel, base_res_factor)
     print(f"\npreprocessing took {time.time() - started:.2f}s\n")
     print(f"rendering {args.n_frames} frames...")
-    if output_file is None and sink is None:
+    if output_file is None and sink is None and rank == 0:
         os.makedirs(output_dir, exist_ok=True)
         stem = lambda path: str(path).split("/")[-1].split(".")[0].lower()
         output_file = f"{output_dir}/{stem(audio_file)}_{stem(ckpt)}_{uuid.uuid4().hex[:8]}.mp4"

@@ -7,6 +7,7 @@ replace nn.Parameters between batches, render.py:160-167 — the cache key track
   * the style-prologue job table (one MauaStyleJob per modulated layer) per batch size
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -16,17 +17,24 @@ from . import _lib as L
 SPLITK_WORKSPACE_BYTES = 64 << 20
 
 
+# precision="mixed": layers whose OUTPUT is at least this wide take their activations as ONE fp16 plane (the "f16"
+# format, include/maua_b200.h) instead of the bf16 (hi, lo) pair.  512 selects the four layers of the 1024^2 generator that
+# are bound by the A-operand fetch of small-N MMAs (Cout <= 64) and carry 47 % of its conv time.
+F16_MIN_RES = int(os.environ.get("MAUA_F16_MIN_RES", "512"))
+
+
 class LayerPlan:
-    __slots__ = ("spec", "job", "rgb_job", "wsq", "w_hi", "w_lo", "s_off", "d_off", "rgb_s_off", "tc_ok")
+    __slots__ = ("spec", "job", "rgb_job", "wsq", "w_hi", "w_lo", "s_off", "d_off", "rgb_s_off", "tc_ok", "fmt", "out_res")
 
 
-def _pack_tc(weight, scale):
+def _pack_tc(weight, scale, fmt="bf16x3"):
     cout, cin, k = weight.shape[1], weight.shape[2], weight.shape[3]
-    hi = torch.empty((k * k, cout, cin), device=weight.device, dtype=torch.bfloat16)
+    dt = torch.float16 if fmt == "f16" else torch.bfloat16
+    hi = torch.empty((k * k, cout, cin), device=weight.device, dtype=dt)
     lo = torch.empty_like(hi)
     with torch.cuda.device(weight.device):
-        L.call("maua_pack_weight_bf16x2", weight.data_ptr(), hi.data_ptr(), lo.data_ptr(), cout, cin, k, float(scale),
-               L.stream_ptr(weight.device))
+        L.call("maua_pack_weight_f16x2" if fmt == "f16" else "maua_pack_weight_bf16x2", weight.data_ptr(), hi.data_ptr(),
+               lo.data_ptr(), cout, cin, k, float(scale), L.stream_ptr(weight.device))
     return hi, lo
 
 
@@ -42,15 +50,20 @@ def build_plan(g, key):
     s_total = 0
     d_total = 0
     n_jobs = 0
-    for sp in g._specs:
+    res = 2
+    for li, sp in enumerate(g._specs):
         lp = LayerPlan()
         lp.spec = sp
         conv = sp.mod.conv
         lp.wsq = _weight_sq(conv.weight, conv.scale)
         lp.tc_ok = g.impl == "tc" and tc_supported(sp.cin, sp.cout)
+        res *= 2 if (sp.up or li == 0) else 1
+        lp.out_res = res  # nominal (bends may change it at run time; synthesize() checks the real shape)
+        lp.fmt = "f16" if (lp.tc_ok and g.precision == "mixed" and res >= F16_MIN_RES) else \
+            ("bf16" if g.precision == "bf16" else "bf16x3")
         lp.w_hi = lp.w_lo = None
         if lp.tc_ok:
-            lp.w_hi, lp.w_lo = _pack_tc(conv.weight, conv.scale)
+            lp.w_hi, lp.w_lo = _pack_tc(conv.weight, conv.scale, lp.fmt)
         lp.job = n_jobs
         n_jobs += 1
         lp.s_off = s_total
@@ -82,6 +95,7 @@ def batch_buffers(g, plan, batch):
     d_buf = torch.empty(plan["d_total"] * batch, device=device, dtype=torch.float32)
     jobs = (L.StyleJob * plan["n_jobs"])()
     views = {}
+    keep = []
     for lp in plan["layers"]:
         sp = lp.spec
         conv = sp.mod.conv
@@ -92,6 +106,12 @@ def batch_buffers(g, plan, batch):
         j.wsq = lp.wsq.data_ptr() if conv.demodulate else None
         j.s_out, j.d_out = s_view.data_ptr(), d_view.data_ptr()
         j.cin, j.cout, j.latent_index = sp.cin, sp.cout, sp.latent_index
+        if lp.fmt == "f16" and conv.demodulate:
+            # fp16 consumers take range-normalised styles (|s| < 1, the power of two moved into d: MauaStyleJob.s_norm_out)
+            s_norm = torch.empty_like(s_view)
+            keep.append(s_norm)
+            j.s_norm_out = s_norm.data_ptr()
+            s_view = s_norm
         views[lp.job] = (s_view, d_view if conv.demodulate else None)
         if sp.rgb is not None:
             rc = sp.rgb.conv
@@ -103,7 +123,7 @@ def batch_buffers(g, plan, batch):
             views[lp.rgb_job] = (rs_view, None)
     raw = bytes(jobs)
     table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
-    bc = {"s_buf": s_buf, "d_buf": d_buf, "table": table, "views": views}
+    bc = {"s_buf": s_buf, "d_buf": d_buf, "table": table, "views": views, "keep": keep}
     plan["batch"][batch] = bc
     return bc
 

@@ -21,6 +21,7 @@ import threading
 import numpy as np
 import torch
 
+from . import _lib as L
 from .stylegan2 import frames_to_u8
 
 
@@ -62,6 +63,7 @@ class FramePipeline:
         self.use_graph = (use_graph and not self.bends and not self.rewrites and not randomize_noise)
         self._graphs = [None, None]
         self._slot_busy = [None, None]  # per ping-pong slot: (d2h-done event, collective work) still reading its frames
+        self.kernels_per_step = 0       # library kernels launched per batch (graph: counted while capturing)
 
     def _graph_slot(self, slot, n):
         """Static inputs + captured forward of one ping-pong slot (created on first use: one eager run, then capture)."""
@@ -83,8 +85,10 @@ class FramePipeline:
         run()
         torch.cuda.current_stream(self.device).synchronize()
         graph = torch.cuda.CUDAGraph()
+        l0 = L.launch_count()
         with torch.cuda.graph(graph):
             gs["out"] = run()
+        self.kernels_per_step = L.launch_count() - l0
         gs["graph"] = graph
         return gs
 
@@ -220,20 +224,27 @@ class FramePipeline:
         for t in item["staged"]:
             t.record_stream(cur)
         self._apply_rewrites(n)
+        l0 = L.launch_count()
         frames, _ = self.g(styles=item["latent"], noise=item["noise"], truncation=item["truncation"],
                            transform_dict_list=item["bends"], randomize_noise=self.randomize_noise,
                            input_is_latent=True, return_u8=True)
+        self.kernels_per_step = L.launch_count() - l0
         return frames  # uint8 [b,H,W,3] on device
 
-    def run(self, consume, gather=None):
+    def run(self, consume, gather=None, ring=None):
         """Render every frame; `consume(np.uint8 [n,H,W,3])` is called in frame order on ranks where it is not None.
 
         world == 1: step i renders batch i.   world > 1: step i renders batches i*world + rank (rank-strided, so one
-        all-gather yields world*B CONSECUTIVE frames); `gather(frames_u8) -> (work, out_u8)` is the
-        collective hook (see parallel.AllGatherFrames).  Short tails are padded by repeating the last frame and
-        trimmed before `consume`.  H2D of step i+1 (copy stream) and D2H of step i-1 (d2h stream) overlap the
-        synthesis of step i (compute stream)."""
-        world, rank = (self.world, self.rank) if gather is not None else (1, 0)
+        step yields world*B CONSECUTIVE frames).  Two ways to bring them to the sink:
+          gather(frames_u8) -> (work, out_u8): ONE NCCL all-gather per step (parallel.AllGatherFrames) — every rank ends up
+              with all frames on the device; without `ring`, rank 0 copies all of them to the host.
+          ring (parallel.HostFrameRing): every rank copies ITS shard device->host into a shared pinned ring over its own
+              PCIe link and rank 0's sink reads the consecutive frames from host memory (no single-link ceiling).
+        Both may be given (the collective then serves on-device consumers only).  Short tails are padded by repeating the
+        last frame and trimmed before `consume`.  H2D of step i+1 (copy stream) and D2H of step i-1 (d2h stream) overlap
+        the synthesis of step i (compute stream); the compute stream never waits for a collective."""
+        sharded = gather is not None or ring is not None
+        world, rank = (self.world, self.rank) if sharded else (1, 0)
         nb = len(self.starts)
         steps = (nb + world - 1) // world
         cur = torch.cuda.current_stream(self.device)
@@ -244,7 +255,12 @@ class FramePipeline:
 
         def finish(p):
             p["done"].synchronize()
-            if consume is not None:
+            if ring is not None:
+                ring.publish(p["step"])
+                if consume is not None:
+                    consume(ring.frames_of(p["step"]).numpy()[:p["valid"]])
+                    ring.release(p["step"])
+            elif consume is not None:
                 consume(p["host"].numpy()[:p["valid"]])
 
         pending = None
@@ -271,7 +287,25 @@ class FramePipeline:
                 work, out = gather(frames, i & 1)   # async collective on NCCL's stream; compute does not wait for it
             else:
                 out = frames
-            if consume is not None:
+            if ring is not None:
+                # sharded D2H: this rank's own frames -> its position in the shared pinned ring (all ranks take part)
+                dst = ring.slot_for_write(i)
+                if pending is not None:
+                    finish(pending)                 # step i-1: publish (and, on rank 0, consume) before queueing more
+                    pending = None
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(ready)
+                    dst.copy_(frames, non_blocking=True)
+                    frames.record_stream(d2h)
+                    done = torch.cuda.Event()
+                    done.record(d2h)
+                self.d2h_bytes += frames.numel()
+                pending = {"done": done, "valid": valid, "step": i}
+                if graph_ok and full:
+                    self._slot_busy[i & 1] = (done, work)
+            elif consume is not None:
                 slot = i & 1
                 if self._host[slot] is None or self._host[slot].shape != out.shape:
                     self._host[slot] = torch.empty(out.shape, dtype=torch.uint8).pin_memory()
@@ -288,13 +322,18 @@ class FramePipeline:
                 self.d2h_bytes += out.numel()
                 if pending is not None:
                     finish(pending)                 # frames of step i-1 (other ping-pong slot)
-                pending = {"done": done, "host": self._host[slot], "valid": valid}
+                pending = {"done": done, "host": self._host[slot], "valid": valid, "step": i}
                 if graph_ok and full:
                     self._slot_busy[i & 1] = (done if gather is None else None, work)
             elif graph_ok and full and work is not None:
                 self._slot_busy[i & 1] = (None, work)
         if pending is not None:
             finish(pending)
+        for slot in (0, 1):   # the last collectives are part of the job: the compute stream joins them before run() returns
+            busy = self._slot_busy[slot]
+            if busy is not None and busy[1] is not None:
+                busy[1].wait()
+                self._slot_busy[slot] = (busy[0], None)
 
 
 class FFmpegSink:
@@ -390,17 +429,34 @@ def fit_frames(frames, out_size):
 
 def render(generator, latents, noise, offset, duration, batch_size, out_size, output_file, audio_file=None,
            truncation=1.0, bends=[], rewrites={}, randomize_noise=False, ffmpeg_preset="slow", sink=None):
+    """Drop-in for the reference's `render.render` (render.py:14-192).  Under torchrun (torch.distributed initialised,
+    see parallel.init_from_env — what `generate(dataparallel=True)` does) the frames are sharded over the ranks of the
+    box: inputs are made identical on every rank (broadcast from rank 0), rank r renders batches i*world + r, one NCCL
+    all-gather of the uint8 frames per step runs beside a sharded device->host copy into a shared pinned ring, and only
+    rank 0 owns the sink / ffmpeg process.  Returns the FramePipeline (its h2d/d2h byte counters are per rank)."""
+    from . import parallel
+
     sizes = {512: (512, 512), 1024: (1024, 1024), 1920: (1920, 1080), 1080: (1080, 1920)}
     if out_size not in sizes:
         raise Exception("The only output sizes currently supported are: 512, 1024, 1080, or 1920")
     w, h = sizes[out_size]
-    own_sink = sink is None
+    rank, world = parallel.current()
+    own_sink = sink is None and rank == 0
     if own_sink:
         sink = FFmpegSink(output_file, w, h, len(latents) / duration, audio_file, offset, duration, ffmpeg_preset)
     if hasattr(generator, "module"):  # th.nn.DataParallel wrapper of the reference CLI (generate_audiovisual.py:54-55)
         generator = generator.module
-    pipe = FramePipeline(generator, latents, list(noise), batch_size, truncation, bends, rewrites, randomize_noise,
-                         fit_size=out_size)
+    noise = list(noise)
+    gather = ring = None
+    if world > 1:
+        device = next(generator.parameters()).device
+        shared = [latents] + noise + [truncation] + [b.get("modulation") for b in bends]
+        shared += [m for _, m in (rewrites or {}).values()]
+        parallel.broadcast_inputs([t for t in shared if torch.is_tensor(t)], device=device)
+        gather = parallel.AllGatherFrames(world)
+        ring = parallel.HostFrameRing(parallel.ring_name(), rank, world, batch_size, (h, w, 3))
+    pipe = FramePipeline(generator, latents, noise, batch_size, truncation, bends, rewrites, randomize_noise,
+                         fit_size=out_size, rank=rank, world=world)
     pipe.warmup()
 
     def consume(frames):
@@ -409,8 +465,12 @@ def render(generator, latents, noise, offset, duration, batch_size, out_size, ou
             f"got: {frames.shape[2]}x{frames.shape[1]}\t\tshould be {w}x{h}")
         sink(frames)
 
-    with torch.no_grad():
-        pipe.run(consume)
+    try:
+        with torch.no_grad():
+            pipe.run(consume if rank == 0 else None, gather, ring)
+    finally:
+        if ring is not None:
+            ring.close()
     if own_sink:
         sink.close()
     return pipe

@@ -352,8 +352,13 @@ class Generator(nn.Module):
         self.size = size
         self.style_dim = style_dim
         self.impl = impl or _impl_default()
-        # "bf16x3": hi*hi + hi*lo + lo*hi (parity grade, ~2^-16 rel);  "bf16": single product (fast, ~1e-2)
+        # "bf16x3": hi*hi + hi*lo + lo*hi on every layer (~2^-16 rel per product; network error ~5e-5)
+        # "mixed"  : as bf16x3 below 512^2; the >= 512^2 layers take ONE fp16 activation plane and the weights as an fp16
+        #            (hi, lo) pair — one tensor-core pass instead of three (network error ~5e-4, inside the 1e-3 parity bar)
+        # "bf16"   : single bf16 product (fast preview, ~1e-2)
         self.precision = precision or os.environ.get("MAUA_TC_PRECISION", "bf16x3")
+        if self.precision not in ("bf16x3", "mixed", "bf16"):
+            raise ValueError(f"precision must be 'bf16x3', 'mixed' or 'bf16', got {self.precision!r}")
 
         layers = [PixelNorm()]
         for _ in range(n_mlp):
@@ -464,6 +469,7 @@ class Generator(nn.Module):
         `(data_ptr, _version)` of every conv / modulation parameter, which in-place ops and `nn.Parameter` replacement
         (render's `rewrites`) bump — edits made through `param.data` (`w.data.mul_()`) do NOT: call this after them."""
         self._plan = None
+        self._synth_handle = None
 
     def _get_plan(self):
         key = self._plan_key()
@@ -526,6 +532,6 @@ class Generator(nn.Module):
         if return_activation_maps:
             return image, acts
         elif return_latents:
-            return image, latent_t
+            return image, (latent_t.get() if hasattr(latent_t, "get") else latent_t)
         else:
             return image, None

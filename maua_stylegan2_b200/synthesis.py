@@ -32,9 +32,14 @@ def _has_bend(layer_id, bends):
     return any(t["layer"] == layer_id for t in bends)
 
 
-def _modulate_split(x, bstride, s, batch):
-    """fp32 NCHW (optionally batch-broadcast) * s[b,c] -> (hi, lo) bf16 NHWC."""
+def _modulate_split(x, bstride, s, batch, fmt="bf16x3"):
+    """fp32 NCHW (optionally batch-broadcast) * s[b,c] -> (hi, lo) bf16 NHWC, or (fp16 plane, None) for fmt "f16"."""
     c, h, w = x.shape[1], x.shape[2], x.shape[3]
+    if fmt == "f16":
+        hi = torch.empty((batch, h, w, c), device=x.device, dtype=torch.float16)
+        L.call("maua_modulate_f16_nhwc", x.data_ptr(), bstride, L.ptr(s), hi.data_ptr(), batch, c, h, w,
+               L.stream_ptr(x.device))
+        return hi, None
     hi = torch.empty((batch, h, w, c), device=x.device, dtype=torch.bfloat16)
     lo = torch.empty_like(hi)
     L.call("maua_modulate_split_nhwc", x.data_ptr(), bstride, L.ptr(s), hi.data_ptr(), lo.data_ptr(), batch, c, h, w,
@@ -42,9 +47,70 @@ def _modulate_split(x, bstride, s, batch):
     return hi, lo
 
 
+_USE_HANDLE = os.environ.get("MAUA_SYNTH_C", "1") == "1"
+
+
+def _synthesize_handle(g, latent, noise, truncation, want_u8):
+    """The whole-forward C ABI (one maua_synth_forward call, csrc/synth.cu) when the call is eligible, else None."""
+    from .stylegan2 import ConstantInput
+    from .synth_handle import SynthHandle
+
+    if not (_USE_HANDLE and g.impl == "tc" and isinstance(g.input, ConstantInput) and L.PROFILE is None):
+        return None
+    device, batch = latent.device, latent.shape[0]
+    mean = g.truncation_latent
+    if mean is None or mean.numel() != g.style_dim or latent.shape[1] < g.n_latent or latent.shape[2] != g.style_dim:
+        return None
+    h = getattr(g, "_synth_handle", None)
+    if h is None or h.key != g._plan_key():
+        try:
+            h = SynthHandle(g)
+        except L.MauaError:
+            g._synth_handle_failed = g._plan_key()
+            return None
+        g._synth_handle = h
+    psi_t, psi_s = None, 1.0
+    if torch.is_tensor(truncation):
+        psi_t = truncation.to(device=device, dtype=torch.float32).contiguous()
+        if psi_t.numel() == 1:
+            psi_t = psi_t.reshape(1).expand(batch).contiguous()
+        elif psi_t.numel() != batch:
+            raise L.MauaError(f"truncation has {psi_t.numel()} entries for a batch of {batch}")
+    else:
+        psi_s = float(truncation)
+    hh, ww = g.input.input.shape[2], g.input.input.shape[3]
+    prepared = []
+    for sp in g._specs:
+        if sp.up:
+            hh, ww = 2 * hh, 2 * ww
+        nz = noise[sp.noise_index]
+        if nz is None:  # randomize_noise=True: fresh N(0,1) per layer (models/stylegan2.py:263-265)
+            nz = torch.randn(batch, 1, hh, ww, device=device)
+        prepared.append(_prep_noise(nz, device, batch, hh * ww))
+    mean = mean.to(device=device, dtype=torch.float32).contiguous()
+    image, u8 = h.forward(latent, prepared, mean, psi_t, psi_s, (hh, ww), want_u8, want_rgb=not want_u8)
+    latent_t = _LazyLatents(h, batch, latent.shape[1], g.style_dim)
+    return (u8 if want_u8 else image), latent_t, []
+
+
+class _LazyLatents:
+    """Truncated latents of a handle forward, copied out of the workspace only if the caller asks (return_latents)."""
+
+    def __init__(self, h, batch, rows, dim):
+        self.args = (h, batch, rows, dim)
+
+    def get(self):
+        h, batch, rows, dim = self.args
+        return h.truncated_latents(batch, rows, dim)
+
+
 def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=False):
     device = latent.device
     batch = latent.shape[0]
+    if not bends and not want_acts:
+        fast = _synthesize_handle(g, latent, noise, truncation, want_u8)
+        if fast is not None:
+            return fast
     plan = g._get_plan()
     with torch.cuda.device(device):
         bc = batch_buffers(g, plan, batch)
@@ -95,7 +161,6 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
         acts = []
         image = None
         layers = plan["layers"]
-        nprod = 1 if g.precision == "bf16" else 3
         current_size = 2  # doubled by every up layer; conv1 runs at 4
         for li, lp in enumerate(layers):
             sp = lp.spec
@@ -112,10 +177,15 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
             # algorithmic work of this layer: conv FLOPs = 2*H_in*W_in*Cin*Cout*9 per sample
             L.TAG = {"layer": li, "up": sp.up, "cin": sp.cin, "cout": sp.cout, "h": in_h, "w": in_w,
                      "flops": 2.0 * in_h * in_w * sp.cin * sp.cout * 9 * batch,
+                     "nprod": {"bf16": 1, "f16": 2, "bf16x3": 3}[lp.fmt] if lp.tc_ok else 1,
                      "out_elems": float(batch) * sp.cout * out_h * out_w}
             if lp.tc_ok:
+                nprod = {"bf16": 1, "f16": 2, "bf16x3": 3}[lp.fmt]
+                if lp.fmt == "f16" and (in_h + (1 if sp.up else 0) < 64 or in_w + (1 if sp.up else 0) < 32):
+                    raise L.MauaError(f"precision='mixed': layer {li} runs at {in_h}x{in_w}, below the 64x32 grid the fp16 "
+                                      "halo kernel needs (a bend shrank it?) - use precision='bf16x3'")
                 if split is None:
-                    split = _modulate_split(x.contiguous(), x_bstride, s, batch)
+                    split = _modulate_split(x.contiguous(), x_bstride, s, batch, lp.fmt)
                 want_split = nxt is not None and nxt.tc_ok and not bend_here
                 # ToRGB fused into the conv epilogue when one CTA sees every output channel (Cout <= 128, halo kernel):
                 # the epilogue emits 3 partial sums per pixel instead of the Cout-channel fp32 map that torgb would re-read
@@ -125,7 +195,9 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
                 want_f32 = want_acts or bend_here or (sp.rgb is not None and not fuse_rgb) or (nxt is not None and not want_split)
                 y = torch.empty((batch, sp.cout, out_h, out_w), device=device, dtype=torch.float32) if want_f32 else None
                 o_hi = o_lo = None
-                if want_split:
+                if want_split and nxt.fmt == "f16":
+                    o_hi = torch.empty((batch, out_h, out_w, sp.cout), device=device, dtype=torch.float16)
+                elif want_split:
                     o_hi = torch.empty((batch, out_h, out_w, sp.cout), device=device, dtype=torch.bfloat16)
                     o_lo = torch.empty_like(o_hi)
                 nzc, nz_bs = _prep_noise(nz, device, batch, out_h * out_w)
@@ -134,6 +206,7 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
                 ep.bias = sp.mod.activate.bias.data_ptr()
                 ep.s_next = bc["views"][nxt.job][0].data_ptr() if want_split else None
                 ep.out_hi, ep.out_lo = L.ptr(o_hi), L.ptr(o_lo)
+                ep.out_fmt = 1 if (want_split and nxt.fmt == "f16") else 0
                 ep.out_f32_nchw = L.ptr(y)
                 ep.slope, ep.act_scale, ep.activate = 0.2, SQRT2, 1
                 ws = plan["workspace"]
@@ -148,14 +221,14 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
                     ep.rgb_w, ep.rgb_out = wr.data_ptr(), rgb_partial.data_ptr()
                 if not sp.up:
                     ep.d = d.data_ptr()
-                    L.call("maua_modconv_tc", split[0].data_ptr(), split[1].data_ptr(), lp.w_hi.data_ptr(),
+                    L.call("maua_modconv_tc", split[0].data_ptr(), L.ptr(split[1]), lp.w_hi.data_ptr(),
                            lp.w_lo.data_ptr(), C.byref(ep), batch, sp.cin, sp.cout, in_h, in_w, 0, nprod, stream)
                 else:
                     u = torch.empty((batch, 2 * in_h + 1, 2 * in_w + 1, sp.cout), device=device, dtype=torch.float32)
                     ep_raw = L.ConvEpilogue()
                     ep_raw.d, ep_raw.out_raw_nhwc, ep_raw.activate = d.data_ptr(), u.data_ptr(), 0
                     ep_raw.workspace, ep_raw.workspace_bytes = ep.workspace, ep.workspace_bytes
-                    L.call("maua_modconv_tc", split[0].data_ptr(), split[1].data_ptr(), lp.w_hi.data_ptr(),
+                    L.call("maua_modconv_tc", split[0].data_ptr(), L.ptr(split[1]), lp.w_hi.data_ptr(),
                            lp.w_lo.data_ptr(), C.byref(ep_raw), batch, sp.cin, sp.cout, in_h, in_w, 1, nprod, stream)
                     L.call("maua_blur_act_nhwc", u.data_ptr(), conv.blur.kernel.data_ptr(), C.byref(ep), batch, sp.cout,
                            2 * in_h + 1, 2 * in_w + 1, stream)

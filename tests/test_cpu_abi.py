@@ -34,14 +34,14 @@ def test_binding_matches_header(lib_path):
 
     bound = set(L.SIGNATURES) | set(L._SPECIAL)
     assert bound == set(declared_symbols())
-    assert L.lib().maua_abi_version() == 1
+    assert L.lib().maua_abi_version() == 2
     assert L.launch_count() == 0  # nothing ran on this GPU-less box
 
 
 def test_struct_layouts_match_c():
     from maua_stylegan2_b200 import _lib as L
 
-    assert ctypes.sizeof(L.StyleJob) == 56
+    assert ctypes.sizeof(L.StyleJob) == 64
     assert ctypes.sizeof(L.ConvEpilogue) == 128
 
 

@@ -39,7 +39,8 @@ def test_conv_kernels_are_tcgen05_tma_tmem_code():
             # CALL.REL = compiler-local subroutines (integer division) are fine; CALL.ABS = an external call (vprintf)
             assert "CALL.ABS" not in body, f"{name}: an external call (printf?) breaks uniform-register MMA issue"
     v2 = {k: v for k, v in _functions(_sass("modconv_tc2.o")).items() if "modconv_tc2_kernel" in k}
-    assert len(v2) == 6                                   # {same-res, transposed} x {1 product, 3 products, concat}
+    # {same-res, transposed} x {bf16: 1 product, 3 products, concat; fp16: two N=BN MMAs, one N=2*BN concat MMA}
+    assert len(v2) == 10
     for name, body in v2.items():
         assert "FFMA2" in body or "FMUL2" in body, name   # packed fp32 epilogue
         # the unrolled R = 4 tap issues its MMAs back to back: at least one run of >= 8 UTCHMMA within 24 instructions

@@ -60,3 +60,41 @@ def test_all_gather_frames_world2_gloo(tmp_path):
         got = np.load(tmp_path / f"rank{r}.npy")
         assert got.shape == want.shape
         assert np.array_equal(got, want), f"rank {r}: frames out of order or duplicated"
+
+
+def _ring_worker(rank, world, port, n_steps, batch, out_dir):
+    from maua_stylegan2_b200.parallel import HostFrameRing
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ring = HostFrameRing(f"maua_test_ring_{port}", rank, world, batch, (4, 6, 3), timeout_s=60)
+    got = []
+    for step in range(n_steps):
+        dst = ring.slot_for_write(step)                       # blocks until rank 0 has consumed step - 2
+        for j in range(batch):
+            dst[j] = _frame((step * world + rank) * batch + j)
+        if step > 0:                                          # the frame loop publishes step i-1 after queueing step i
+            ring.publish(step - 1)
+            if rank == 0:
+                got.append(ring.frames_of(step - 1).clone())
+                ring.release(step - 1)
+    ring.publish(n_steps - 1)
+    if rank == 0:
+        got.append(ring.frames_of(n_steps - 1).clone())
+        ring.release(n_steps - 1)
+        np.save(os.path.join(out_dir, "ring.npy"), torch.cat(got).numpy())
+    ring.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_host_frame_ring_world2_gloo(tmp_path):
+    """Sharded D2H path: every rank writes its shard of each step into the shared two-slot ring, rank 0 reads world*B
+    consecutive frames per step; the counters keep writers from overwriting a slot rank 0 has not consumed."""
+    n_steps, batch, world = 9, 3, 2
+    port = _free_port()
+    mp.spawn(_ring_worker, args=(world, port, n_steps, batch, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "ring.npy")
+    want = torch.stack([_frame(i) for i in range(n_steps * world * batch)]).numpy()
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert not os.path.exists(f"/dev/shm/maua_test_ring_{port}")

@@ -34,18 +34,18 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2])
-def test_nccl_sharded_frames_equal_single_gpu(tmp_path, world):
+@pytest.mark.parametrize("world,mode", [(2, "render"), (2, "gather")])
+def test_nccl_sharded_frames_equal_single_gpu(tmp_path, world, mode):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, this box has {torch.cuda.device_count()}")
     from maua_stylegan2_b200.render import FramePipeline
     from tests.util import make_generator
 
-    size, cm, n_frames, batch = 256, 1, 45, 4     # 11 full batches + a tail of 1: uneven over 2 ranks
+    size, cm, n_frames, batch = 512, 1, 45, 4     # 11 full batches + a tail of 1: uneven over 2 ranks
     out_file = str(tmp_path / "frames.npy")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "nccl_frames_worker.py"), out_file,
-           str(size), str(cm), str(n_frames), str(batch)]
+           str(size), str(cm), str(n_frames), str(batch), mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     multi = np.load(out_file)

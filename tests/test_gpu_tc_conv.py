@@ -13,26 +13,32 @@ from tests.util import rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _pack(w, scale):
+def _pack(w, scale, fmt="bf16x3"):
     from maua_stylegan2_b200.plan import _pack_tc
 
-    return _pack_tc(w[None].contiguous(), scale)
+    return _pack_tc(w[None].contiguous(), scale, fmt)
 
 
-def _run_tc(x, w, s, d, noise, nw, bias, s_next, up, nprod, scale, workspace=None):
+def _run_tc(x, w, s, d, noise, nw, bias, s_next, up, nprod, scale, workspace=None, out_f16=False):
+    """nprod 3 / 1: bf16 (hi, lo) activations; nprod 2: the "f16" format (one fp16 activation plane, fp16 weight pair).
+    out_f16: the epilogue writes the consumer's activations as one fp16 plane (returned as o_hi, o_lo = zeros)."""
     from maua_stylegan2_b200 import _lib as L
     from maua_stylegan2_b200.synthesis import _modulate_split
 
     b, cin, h, wd = x.shape
     cout = w.shape[0]
-    w_hi, w_lo = _pack(w, scale)
-    hi, lo = _modulate_split(x, x[0].numel(), s, b)
+    fmt = "f16" if nprod == 2 else "bf16x3"
+    w_hi, w_lo = _pack(w, scale, fmt)
+    hi, lo = _modulate_split(x, x[0].numel(), s, b, fmt)
+    if lo is None:
+        lo = hi   # ignored by the kernel
     stream = L.stream_ptr(x.device)
     oh, ow = (2 * h, 2 * wd) if up else (h, wd)
     y = torch.full((b, cout, oh, ow), float("nan"), device="cuda")
-    o_hi = torch.zeros((b, oh, ow, cout), device="cuda", dtype=torch.bfloat16)
+    o_hi = torch.zeros((b, oh, ow, cout), device="cuda", dtype=torch.float16 if out_f16 else torch.bfloat16)
     o_lo = torch.zeros_like(o_hi)
     ep = L.ConvEpilogue()
+    ep.out_fmt = 1 if out_f16 else 0
     ep.noise, ep.noise_weight = noise.data_ptr(), nw.data_ptr()
     ep.noise_bstride = oh * ow if noise.shape[0] == b else 0
     ep.bias, ep.s_next = bias.data_ptr(), s_next.data_ptr()
@@ -202,6 +208,73 @@ def test_tc2_forced_configurations(case, forces, monkeypatch):
     monkeypatch.setenv("MAUA_TC_FORCE", "4,256,1,1")
     with pytest.raises(L.MauaError):
         _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 3, scale)
+
+
+# The "f16" activation format (precision="mixed": the >= 512^2 layers): one fp16 activation plane, fp16 (hi, lo) weights.
+# The only rounding is the 11-bit activation operand: per-layer error ~2e-4 of the tensor max (bar: 6e-4 here, 1e-3 on
+# the network); the fp16 OUTPUT plane adds the consumer's own operand rounding (2^-11 per element).
+F16_CASES = [
+    ((2, 64, 32, 128, 64, False), None),         # mode 4 (concat N = 2*BN), R=4
+    ((1, 64, 64, 96, 64, False), None),          # mode 4, BN=64
+    ((1, 128, 128, 64, 64, False), None),        # mode 3 (two N=BN MMAs into one accumulator)
+    ((1, 64, 256, 64, 32, False), None),         # mode 3, BN=256
+    ((2, 64, 32, 72, 40, True), None),           # up, mode 4
+    ((1, 128, 64, 64, 48, True), None),          # up, BN=64
+    ((1, 128, 128, 64, 32, True), None),         # up, mode 3
+    ((2, 64, 32, 64, 40, False), ["1,32,1,1", "2,32,0,1", "4,16,1,1"]),
+    ((2, 64, 32, 56, 24, True), ["1,32,1,1", "2,32,1,2", "4,32,0,4", "2,32,0,1"]),
+]
+
+
+@pytest.mark.parametrize("case,forces", F16_CASES)
+def test_tc2_f16_activation_format(case, forces, monkeypatch):
+    from maua_stylegan2_b200 import _lib as L
+
+    b, cin, cout, h, w, up = case
+    x, wt, s, d, noise, nw, bias, s_next, scale = _case_tensors(b, cin, cout, h, w, up, 300 + cin + cout + h)
+    ref, raw = _reference(x, wt, s, d, noise, nw, bias, up, scale)
+    for f in (forces or [None]):
+        if f is not None:
+            monkeypatch.setenv("MAUA_TC_FORCE", f)
+        for out_f16 in (False, True):
+            y, o_hi, o_lo, u = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 2, scale, out_f16=out_f16)
+            cfg = L.last_conv_config()
+            assert cfg.startswith("v2 ") and " prod=2 " in cfg, cfg
+            if up:
+                assert rel_err(u.cpu().numpy(), raw.numpy()) < 6e-4, "raw transposed-conv phases"
+            assert not torch.isnan(y).any()
+            e = rel_err(y.cpu().numpy(), ref.numpy())
+            rec = (o_hi.float() + (0 if out_f16 else o_lo.float())).permute(0, 3, 1, 2).cpu().double() \
+                / s_next.cpu().double()[:, :, None, None]
+            e2 = rel_err(rec.numpy(), ref.numpy())
+            print(f"{case} force={f} out_f16={out_f16}: {cfg.split(' items')[0]}  fp32 out {e:.2e}  split out {e2:.2e}")
+            assert e < 6e-4, f"fp32 NCHW output rel err {e}"
+            assert e2 < (1.2e-3 if out_f16 else 6e-4), f"NHWC output rel err {e2}"
+    # the fp16 format needs the halo kernel: tiny layers must refuse it loudly instead of running something else
+    monkeypatch.delenv("MAUA_TC_FORCE", raising=False)
+    xs, wts, ss, ds, ns, nws, bs, sns, sc = _case_tensors(2, 64, 64, 16, 16, False, 1)
+    with pytest.raises(L.MauaError):
+        _run_tc(xs, wts, ss, ds, ns, nws, bs, sns, False, 2, sc)
+
+
+def test_f16_layout_kernels():
+    from maua_stylegan2_b200.synthesis import _modulate_split
+
+    torch.manual_seed(8)
+    x = torch.randn(3, 40, 5, 7, device="cuda") * 50
+    x[0, 0, 0, 0] = 1e6          # saturates to the largest finite fp16 instead of overflowing to inf
+    s = torch.randn(3, 40, device="cuda")
+    s[0, 0] = 1.0
+    hi, lo = _modulate_split(x, x[0].numel(), s, 3, "f16")
+    assert lo is None and hi.dtype == torch.float16
+    want = (x * s[:, :, None, None]).permute(0, 2, 3, 1).clamp(-65504, 65504)
+    assert torch.equal(hi, want.to(torch.float16))
+    assert torch.isfinite(hi.float()).all() and hi[0, 0, 0, 0] == 65504
+    w = torch.randn(1, 24, 40, 3, 3, device="cuda")
+    w_hi, w_lo = _pack(w[0], 0.25, "f16")
+    wantw = (w[0] * 0.25).permute(2, 3, 0, 1).reshape(9, 24, 40)
+    assert w_hi.dtype == torch.float16 and torch.equal(w_hi, wantw.to(torch.float16))
+    assert (w_hi.float() + w_lo.float() - wantw).abs().max() <= wantw.abs().max() * 2 ** -20
 
 
 def test_tc2_fused_torgb_partial_sums():

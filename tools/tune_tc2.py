@@ -19,6 +19,9 @@ ap.add_argument("--reps", type=int, default=8)
 ap.add_argument("--only", default=None, help="'cin,cout,h,up': run just this layer with the policy's configuration "
                                              "(or --force 'R,BN,cat,groups'), no sweep — the ncu capture target")
 ap.add_argument("--force", default=None)
+ap.add_argument("--prod", type=int, default=3, help="3 = split bf16, 2 = fp16 activation format, 1 = single bf16 product")
+ap.add_argument("--min-res", type=int, default=64, help="only layers whose output is at least this wide")
+ap.add_argument("--out-f16", type=int, default=-1, help="epilogue output format (default: fp16 plane iff --prod 2)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 chan = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * a.cm, 128: 128 * a.cm, 256: 64 * a.cm, 512: 32 * a.cm,
@@ -38,10 +41,12 @@ def run(cin, cout, h, up, fuse, last, force):
         os.environ.pop("MAUA_TC_FORCE", None)
     else:
         os.environ["MAUA_TC_FORCE"] = "%d,%d,%d,%d" % force
-    x_hi = torch.randn(B, h, h, cin, device=dev).bfloat16()
-    x_lo = (torch.randn(B, h, h, cin, device=dev) * 2 ** -9).bfloat16()
-    w_hi = torch.randn(9, cout, cin, device=dev).bfloat16()
-    w_lo = (torch.randn(9, cout, cin, device=dev) * 2 ** -9).bfloat16()
+    dt = torch.float16 if a.prod == 2 else torch.bfloat16
+    x_hi = torch.randn(B, h, h, cin, device=dev).to(dt)
+    x_lo = (torch.randn(B, h, h, cin, device=dev) * 2 ** -9).to(dt)
+    w_hi = torch.randn(9, cout, cin, device=dev).to(dt)
+    w_lo = (torch.randn(9, cout, cin, device=dev) * 2 ** -9).to(dt)
+    out_f16 = (a.prod == 2) if a.out_f16 < 0 else bool(a.out_f16)
     d = torch.rand(B, cout, device=dev) + 0.5
     ep = L.ConvEpilogue()
     ep.d = d.data_ptr()
@@ -55,8 +60,9 @@ def run(cin, cout, h, up, fuse, last, force):
         nw = torch.tensor([0.1], device=dev)
         bias = torch.zeros(cout, device=dev)
         sn = torch.ones(B, cout, device=dev)
-        o_hi = torch.empty(B, h, h, cout, device=dev, dtype=torch.bfloat16)
+        o_hi = torch.empty(B, h, h, cout, device=dev, dtype=torch.float16 if out_f16 else torch.bfloat16)
         o_lo = torch.empty_like(o_hi)
+        ep.out_fmt = 1 if out_f16 else 0
         ep.noise, ep.noise_weight, ep.noise_bstride = nz.data_ptr(), nw.data_ptr(), h * h
         ep.bias = bias.data_ptr()
         if not last:  # the last layer only feeds ToRGB
@@ -75,7 +81,7 @@ def run(cin, cout, h, up, fuse, last, force):
 
     def launch():
         L.call("maua_modconv_tc", x_hi.data_ptr(), x_lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), C.byref(ep), B, cin,
-               cout, h, h, 1 if up else 0, 3, stream)
+               cout, h, h, 1 if up else 0, a.prod, stream)
 
     try:
         launch()
@@ -100,6 +106,8 @@ if a.only:
     sys.exit(0)
 
 for cin, cout, h, up, fuse, last in layers:
+    if (2 * h if up else h) < a.min_res:
+        continue
     flops = 2.0 * h * h * cin * cout * 9 * B
     base = run(cin, cout, h, up, fuse, last, None)
     rows = []
