@@ -206,14 +206,16 @@ typedef struct MauaConvEpilogue {
  *   n_products: 3 = split bf16 (hi*hi + hi*lo + lo*hi), 1 = bf16 hi*hi only (fast, ~1e-2),
  *               2 = fp16: x_hi is ONE fp16 plane (x_lo ignored), w_hi/w_lo the fp16 pair (halo kernel only: H,W >= 64x32).
  *   up == 0: same resolution, zero pad 1, fused epilogue (demod, noise, bias, lrelu, next-style, split)
- *   up == 1: stride-2 transposed conv evaluated as 4 sub-pixel phases; writes ep->out_raw_nhwc (demod applied).
+ *   up == 1: stride-2 transposed conv evaluated as 4 sub-pixel phases; writes ep->out_raw_nhwc (times ep->d if given).
  * Requirements: Cin % 32 == 0, Cout % 16 == 0, Cout >= 16.  `ep` is a HOST pointer (copied at launch). */
 int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                     const MauaConvEpilogue* ep_host, int batch, int cin, int cout, int h, int w, int up,
                     int n_products, void* stream);
 
-/* u [B,Hu,Wu,C] fp32 (Hu = 2H+1) -> 4x4 FIR k4 with pad (1,1) -> [B,Hu-1,Wu-1,C], then the activation
- * epilogue of `ep` (noise, bias, lrelu, s_next, split / fp32 NCHW).  ep->d is ignored (already applied). */
+/* u [B,Hu,Wu,C] fp32 (Hu = 2H+1) -> 4x4 FIR k4 with pad (1,1) -> [B,Hu-1,Wu-1,C], then * ep->d[b,c] when ep->d is not
+ * NULL (demodulation commutes with the per-channel FIR: pass the transposed conv a NULL d and give it here, so that the
+ * conv epilogue streams its raw phases from TMEM to HBM), then the activation epilogue of `ep` (noise, bias, lrelu,
+ * s_next, split / fp16 plane / fp32 NCHW). */
 int maua_blur_act_nhwc(const float* u, const float* k4, const MauaConvEpilogue* ep_host, int batch, int ch, int hu,
                        int wu, void* stream);
 

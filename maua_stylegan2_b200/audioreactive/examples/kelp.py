@@ -3,10 +3,10 @@ audioreactive/examples/kelp.py).
 
 Sections of the track get their own spline loop through four latents (two sets: calm / drop, blended by the RMS
 envelope); noise is tileable-in-time Perlin noise that loops every two bars, a high-frequency field faded in by the RMS.
-The reference finds the sections with `laplacian_segmentation` (librosa beat tracking + spectral clustering, out of scope
-on the device path — SURVEY.md §8(f) row 4) and the drum envelopes from private multitrack stems; here sections fall
-on a fixed 16-bar grid unless `args.sections = (timestamps, labels)` is supplied, and the envelopes come from the
-mix through band-limited onsets."""
+Like the reference, the sections come from `ar.laplacian_segmentation` (audioreactive/segmentation.py: device STFT /
+constant-Q / MFCC front-end, host spectral clustering) unless `args.sections = (timestamps, labels)` is supplied; the
+reference takes the drum envelopes from private multitrack stems, here they come from the mix through band-limited
+onsets."""
 import os
 
 import numpy as np
@@ -31,8 +31,15 @@ def initialize(args):
 
 
 def sections(args):
+    """(timestamps incl. the end of the clip, labels): `args.sections` if the caller supplies them, else the reference's
+    `ar.laplacian_segmentation(args.audio, args.sr, k=7)` (kelp.py:44-47), else a fixed 16-bar grid (clips too short to
+    segment)."""
     if getattr(args, "sections", None) is not None:
         return args.sections
+    stamps, labels = ar.laplacian_segmentation(args.audio, args.sr, k=7)
+    stamps = [t for t in stamps if t < args.duration]
+    if len(stamps) >= 2:
+        return stamps + [args.duration], labels[:len(stamps)]
     bar = 4 * 60 / BPM
     stamps = list(np.arange(0, args.duration, 16 * bar)) + [args.duration]
     return stamps, [i % 7 for i in range(len(stamps) - 1)]

@@ -11,7 +11,7 @@ Differences from the reference, all forced by its un-vendored dependencies (SURV
     libraries' published algorithms.
   * `chroma`: the CQT front-end of chroma_cens is replaced by the STFT chroma filterbank (north_star: cuFFT-fronted);
     CENS post-processing and the cosine k-NN median filter follow the published librosa algorithms.
-  * `laplacian_segmentation` is out of scope.
+  * `laplacian_segmentation` lives in segmentation.py (device front-end, host spectral clustering).
 """
 import math
 import os

@@ -251,24 +251,33 @@ __global__ void cens_quant_kernel(const float* __restrict__ raw, float* __restri
   }
 }
 
+// (C <= 16 accumulators live in registers: the loops over c are fully unrolled and guarded, a runtime-indexed acc[] went to
+//  local memory: 36 STL in the round-1 SASS)
 __global__ void cens_smooth_kernel(const float* __restrict__ q, float* __restrict__ out, int T, int C, int win_len) {
   // hann(win_len, symmetric) / sum, 'same' convolution with zero boundary, then L2 normalisation over C
   const int t = blockIdx.x * 256 + threadIdx.x;
   if (t >= T) return;
   float acc[16];
-  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
   float wsum = 0.f;
   for (int j = 0; j < win_len; ++j) wsum += 0.5f - 0.5f * cospif(2.f * j / (win_len - 1));
   for (int j = 0; j < win_len; ++j) {
     const int tt = t + j - win_len / 2;
     if (tt < 0 || tt >= T) continue;
     const float w = (0.5f - 0.5f * cospif(2.f * j / (win_len - 1))) / wsum;
-    for (int c = 0; c < C; ++c) acc[c] = fmaf(q[(long long)tt * C + c], w, acc[c]);
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < C) acc[c] = fmaf(q[(long long)tt * C + c], w, acc[c]);
   }
   float n2 = 0.f;
-  for (int c = 0; c < C; ++c) n2 = fmaf(acc[c], acc[c], n2);
+#pragma unroll
+  for (int c = 0; c < 16; ++c)
+    if (c < C) n2 = fmaf(acc[c], acc[c], n2);
   n2 = fmaxf(sqrtf(n2), 1.17549435e-38f);
-  for (int c = 0; c < C; ++c) out[(long long)t * C + c] = acc[c] / n2;
+#pragma unroll
+  for (int c = 0; c < 16; ++c)
+    if (c < C) out[(long long)t * C + c] = acc[c] / n2;
 }
 
 // One block per frame i: cosine distances to every other frame into scratch, k-th smallest by bisection on the
@@ -500,18 +509,25 @@ __global__ void minmax_clip_kernel(const float* __restrict__ ref, int n_ref, flo
 }
 
 // sequential IIR (scipy.signal.sosfilt, direct form II transposed), double precision, one thread
+template <int NS>
 __global__ void sosfilt_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
-                               const double* __restrict__ sos, int n_sections) {
+                               const double* __restrict__ sos) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double z0[16], z1[16];
-  for (int s = 0; s < n_sections; ++s) z0[s] = z1[s] = 0.0;
+  // section state and coefficients in registers (NS is a compile-time constant: no local-memory arrays)
+  double z0[NS], z1[NS], c0[NS], c1[NS], c2[NS], c4[NS], c5[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    z0[s] = z1[s] = 0.0;
+    const double* c = sos + 6 * s;  // b0 b1 b2 a0 a1 a2 (a0 == 1)
+    c0[s] = c[0]; c1[s] = c[1]; c2[s] = c[2]; c4[s] = c[4]; c5[s] = c[5];
+  }
   for (long long i = 0; i < n; ++i) {
     double v = (double)x[i];
-    for (int s = 0; s < n_sections; ++s) {
-      const double* c = sos + 6 * s;  // b0 b1 b2 a0 a1 a2 (a0 == 1)
-      const double o = c[0] * v + z0[s];
-      z0[s] = c[1] * v - c[4] * o + z1[s];
-      z1[s] = c[2] * v - c[5] * o;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const double o = c0[s] * v + z0[s];
+      z0[s] = c1[s] * v - c4[s] * o + z1[s];
+      z1[s] = c2[s] * v - c5[s] * o;
       v = o;
     }
     y[i] = (float)v;
@@ -880,7 +896,14 @@ extern "C" int maua_percentile_clip_f32(const float* x, float* y, int n, float p
 extern "C" int maua_sosfilt_f32(const float* x, float* y, long long n, const double* sos, int n_sections,
                                 void* stream) {
   MAUA_CHECK_ARG(x && y && sos && n >= 1 && n_sections >= 1 && n_sections <= 16, "sosfilt: bad arguments");
-  sosfilt_kernel<<<1, 32, 0, as_stream(stream)>>>(x, y, n, sos, n_sections);
+  cudaStream_t st = as_stream(stream);
+  switch (n_sections) {   // the butter(12, bandpass) of audioreactive.rms has 12 sections; other orders are rare
+#define MAUA_SOS_CASE(N) case N: sosfilt_kernel<N><<<1, 32, 0, st>>>(x, y, n, sos); break;
+    MAUA_SOS_CASE(1) MAUA_SOS_CASE(2) MAUA_SOS_CASE(3) MAUA_SOS_CASE(4) MAUA_SOS_CASE(5) MAUA_SOS_CASE(6) MAUA_SOS_CASE(7)
+    MAUA_SOS_CASE(8) MAUA_SOS_CASE(9) MAUA_SOS_CASE(10) MAUA_SOS_CASE(11) MAUA_SOS_CASE(12) MAUA_SOS_CASE(13)
+    MAUA_SOS_CASE(14) MAUA_SOS_CASE(15) MAUA_SOS_CASE(16)
+#undef MAUA_SOS_CASE
+  }
   MAUA_CHECK_LAUNCH("sosfilt");
   return MAUA_OK;
 }

@@ -4,6 +4,8 @@
 // :262-266 NoiseInjection, op/fused_act.py:82-97): the transposed-conv kernel leaves u = d * convT(x) as fp32
 // [B, 2H+1, 2W+1, C]; this kernel computes
 //     o[b,oy,ox,c] = sum_{a,e<4} Kf[a][e] * u[b, oy+a-1, ox+e-1, c]        (Kf = flipped FIR, zero outside u)
+//     o = o * d[b,c]                    (optional: demodulation commutes with the per-channel FIR, so the conv kernel
+//                                        writes the raw phases and its epilogue needs no per-channel operand at all)
 //     o = lrelu(o + nw*noise[b,oy,ox] + bias[c]) * sqrt2
 // and writes what the next layer consumes: (hi, lo) bf16 NHWC of o * s_next[b,c] and/or fp32 NCHW o.
 // HBM-bound: 4 B/elt in, 4 B/elt out.  One CTA = 16x16 output pixels x 32 channels; the 19x19x32 input tile
@@ -82,8 +84,9 @@ __global__ void __launch_bounds__(256) blur_act_nhwc_kernel(const float* __restr
 
   const int ox = ox0 + lx;
   if (ox >= ow) return;
-  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), sn = make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), sn = make_float4(1.f, 1.f, 1.f, 1.f), dm = sn;
   float nw = 0.f;
+  if (ep.d) dm = __ldg(reinterpret_cast<const float4*>(ep.d + (long long)b * ch + cbase));
   if (ep.activate) {
     if (ep.bias) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + cbase));
     if (ep.noise) nw = __ldg(ep.noise_weight);
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(256) blur_act_nhwc_kernel(const float* __restr
   for (int j = 0; j < 8; ++j) {
     const int oy = oy0 + ly0 + j;
     if (oy >= oh) break;
-    float v[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
+    float v[4] = {__fmul_rn(acc[j].x, dm.x), __fmul_rn(acc[j].y, dm.y), __fmul_rn(acc[j].z, dm.z), __fmul_rn(acc[j].w, dm.w)};
     if (ep.activate) {
       float nz = 0.f;
       if (ep.noise) nz = __fmul_rn(nw, __ldg(ep.noise + (long long)b * ep.noise_bstride + (long long)oy * ow + ox));
@@ -204,13 +207,14 @@ __global__ void __launch_bounds__(128 * (16 / RPT), 2) blur_act_nhwc_tma_kernel(
     decode(t, cg, ox0, oy0, b);
     const int cbase = cg * BCH + c4 * 4;
     const int ox = ox0 + lx;
-    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), sn = make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), sn = make_float4(1.f, 1.f, 1.f, 1.f), dm = sn;
     float nzv[RPT];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) nzv[j] = 0.f;
     if (ox < ow) {
       if (ep.activate && ep.bias) bias = __ldg(reinterpret_cast<const float4*>(ep.bias + cbase));
       if (ep.s_next) sn = __ldg(reinterpret_cast<const float4*>(ep.s_next + (long long)b * ch + cbase));
+      if (ep.d) dm = __ldg(reinterpret_cast<const float4*>(ep.d + (long long)b * ch + cbase));
       if (ep.activate && ep.noise) {
         const float* np = ep.noise + (long long)b * ep.noise_bstride + (long long)(oy0 + ly0) * ow + ox;
 #pragma unroll
@@ -254,7 +258,9 @@ __global__ void __launch_bounds__(128 * (16 / RPT), 2) blur_act_nhwc_tma_kernel(
     for (int j = 0; j < RPT; ++j) {
       const int oy = oy0 + ly0 + j;
       if (oy >= oh) break;
-      float v0 = acc[j].x, v1 = acc[j].y, v2 = acc[j].z, v3 = acc[j].w;
+      // demodulation d[b,c] (when the transposed conv left it to this kernel): it commutes with the per-channel FIR
+      float v0 = __fmul_rn(acc[j].x, dm.x), v1 = __fmul_rn(acc[j].y, dm.y), v2 = __fmul_rn(acc[j].z, dm.z),
+            v3 = __fmul_rn(acc[j].w, dm.w);
       if (ep.activate) {
         const float nz = __fmul_rn(nw, nzv[j]);
         v0 = lrelu_scaled(__fadd_rn(__fadd_rn(v0, nz), bias.x), ep.slope, ep.act_scale);

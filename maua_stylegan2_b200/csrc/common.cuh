@@ -118,6 +118,19 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   return d;
 }
 
+// 256-bit global store (sm_100: STG.E.ENL2.256): 8 consecutive floats, address 32-byte aligned
+__device__ __forceinline__ void st_global_v8(float* p, float2 a, float2 b, float2 c, float2 d) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x),
+               "f"(c.y), "f"(d.x), "f"(d.y)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_v8_b32(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                                 uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5),
+               "r"(a6), "r"(a7)
+               : "memory");
+}
+
 __device__ __forceinline__ float lrelu_scaled(float v, float slope, float scale) {
   return __fmul_rn(v > 0.f ? v : __fmul_rn(v, slope), scale);
 }

@@ -26,8 +26,16 @@ namespace maua {
 namespace tc2 {
 
 constexpr int TH = 16, TW = 8;  // one M tile = 16 rows x 8 columns
-constexpr int EPI_GROUPS = 3;   // epilogue warps = 4 * EPI_GROUPS (each TMEM lane quadrant is served by EPI_GROUPS warps)
-constexpr int THREADS = 64 + 128 * EPI_GROUPS;
+// Epilogue warps = 4 * EPI_GROUPS (each TMEM lane quadrant is served by EPI_GROUPS warps).
+//   EPI_GROUPS = 3 (default): 2 role warps + 12 epilogue warps = 448 threads, 128 registers each.
+//   EPI_GROUPS = 4 (-DMAUA_EPI_GROUPS=4): the role warps get a warpgroup of their own (warps 0-3) and hand registers to the
+//   16 epilogue warps with setmaxnreg (a plain 640-thread launch caps every thread at 96 registers).
+#ifndef MAUA_EPI_GROUPS
+#define MAUA_EPI_GROUPS 3
+#endif
+constexpr int EPI_GROUPS = MAUA_EPI_GROUPS;
+constexpr int ROLE_WARPS = EPI_GROUPS >= 4 ? 4 : 2;   // warps before the first epilogue warp
+constexpr int THREADS = 32 * ROLE_WARPS + 128 * EPI_GROUPS;
 
 struct Params {
   int B, H, W, Cin, Cout;
@@ -145,6 +153,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const uint32_t acc_cols = (uint32_t)(p.n_phase * p.R) * blk_cols;  // ... of one accumulator stage
   const uint32_t halo_bytes = (uint32_t)(p.HW_ * p.HH_) * ROW;    // bytes one TMA box writes per plane
 
+  if (EPI_GROUPS >= 4) {  // register hand-over between warpgroups (all warps of a warpgroup execute the same instruction)
+    if (warp < ROLE_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+  }
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer ================================
     int ia = 0, ib = 0;
@@ -265,15 +277,18 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       if (leader) umma_commit(acc_full + 8 * as);
       if (++as == p.AS) { as = 0; pacc ^= 1; }
     }
-  } else if (warp >= 2) {
+  } else if (warp >= ROLE_WARPS) {
     // ================================ epilogue ================================
     // 4*EPI_GROUPS warps: warp w serves TMEM lane quadrant (w & 3); the 16-column chunks of all accumulators of an
     // item are dealt round-robin to the EPI_GROUPS warps of a quadrant (a lone warp per scheduler exposes every latency)
     const int quad = warp & 3;
-    const int egroup = (warp - 2) >> 2;
+    const int egroup = (warp - ROLE_WARPS) >> 2;
     const int m = quad * 32 + lane;
     const int tx = m & (TW - 1), ty = m >> 3;
-    const float nwv = (!UP && ep.activate && ep.noise) ? __ldg(ep.noise_weight) : 0.f;
+    // activation gain folded into the staged vectors (see the staging loop); slope outside [0, 1] keeps the generic form
+    const bool fold_gain = ep.activate != 0 && ep.act_scale > 0.f && ep.slope >= 0.f && ep.slope <= 1.f;
+    const float gain = fold_gain ? ep.act_scale : 1.f;
+    const float nwv = (!UP && ep.activate && ep.noise) ? __ldg(ep.noise_weight) * gain : 0.f;
     int as = 0;
     uint32_t pacc = 0;
     // Hot-loop parameters pinned in registers: ptxas otherwise re-reads them from the constant bank inside the job loop
@@ -305,10 +320,14 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       decode(item, n0, grp, x0, y0, b);
       if (!UP && b != cur_b) {  // uniform over the epilogue warps: they all walk the same item sequence
         asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_GROUPS) : "memory");  // nobody still reads the old vectors
-        const int et = (int)threadIdx.x - 64;
+        const int et = (int)threadIdx.x - 32 * ROLE_WARPS;
+        // lrelu(x) * g = max(x * g, slope * x * g) for g > 0, 0 <= slope <= 1: the activation gain g is folded into the
+        // staged demodulation / bias vectors (and the noise scalar), which removes one multiply per element and turns the
+        // compare + select pairs into single FMNMX instructions (the epilogue, not the tensor pipe, paces the Cout <= 64
+        // layers: ncu, 32->32 @1024^2, 0.64 eligible warps per scheduler)
         for (int i = et; i < Cout; i += 128 * EPI_GROUPS) {
-          sm_d[i] = ep.d ? __ldg(ep.d + (long long)b * Cout + i) : 1.f;
-          sm_b[i] = (act && ep.bias) ? __ldg(ep.bias + i) : 0.f;
+          sm_d[i] = (ep.d ? __ldg(ep.d + (long long)b * Cout + i) : 1.f) * gain;
+          sm_b[i] = (act && ep.bias) ? __ldg(ep.bias + i) * gain : 0.f;
           sm_s[i] = ep.s_next ? __ldg(ep.s_next + (long long)b * Cout + i) : 1.f;
         }
         if (fuse_rgb)
@@ -358,11 +377,12 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         float2 rgb0 = make_float2(0.f, 0.f), rgb1 = rgb0, rgb2 = rgb0;
 #pragma unroll 1
         for (int c = c_first; c < c_end; c += 16) {   // a single iteration unless ToRGB is fused
+          // transposed conv: demodulation is normally left to maua_blur_act_nhwc (it commutes with the per-channel FIR),
+          // so the raw phases go straight from TMEM to HBM; ep.d != NULL keeps the multiply here (stand-alone use)
           float4 dup[4];
-          if (UP) {
+          if (UP && dglob) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              dup[q] = dglob ? __ldg(reinterpret_cast<const float4*>(dglob + c) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+            for (int q = 0; q < 4; ++q) dup[q] = __ldg(reinterpret_cast<const float4*>(dglob + c) + q);
           }
           uint32_t rr[16];
           if (p.dbg & 8) {
@@ -370,6 +390,15 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             for (int i = 0; i < 16; ++i) rr[i] = (uint32_t)(c + i + lane);
           } else {
             tmem_ld_x16(lane_addr + acc_col + (uint32_t)c, rr);
+          }
+          // per-channel operands of this chunk, requested while the TMEM loads are in flight
+          float4 dv[4], bv[4];
+          if (!UP) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              dv[q] = dptr[(c >> 2) + q];
+              bv[q] = bptr[(c >> 2) + q];
+            }
           }
           float2 v[8];
           if (cat && !(p.dbg & 8)) {
@@ -390,30 +419,39 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           // stream, not the tensor pipe, paced the Cout <= 128 layers (ncu: 263 SASS instructions per 16-column chunk,
           // 160 of them scalar FADD/FMUL/FFMA) — the pairs below halve that part.
           if (UP) {
+            if (dglob) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              v[2 * q] = fmul2(v[2 * q], make_float2(dup[q].x, dup[q].y));
-              v[2 * q + 1] = fmul2(v[2 * q + 1], make_float2(dup[q].z, dup[q].w));
+              for (int q = 0; q < 4; ++q) {
+                v[2 * q] = fmul2(v[2 * q], make_float2(dup[q].x, dup[q].y));
+                v[2 * q + 1] = fmul2(v[2 * q + 1], make_float2(dup[q].z, dup[q].w));
+              }
             }
-            float4* dst = reinterpret_cast<float4*>(ep.out_raw_nhwc + pix * Cout + n0 + c);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[2 * i].x, v[2 * i].y, v[2 * i + 1].x, v[2 * i + 1].y);
+            // 64 contiguous bytes per lane as TWO 256-bit stores: whole 32-byte sectors per request (four 128-bit stores
+            // produced half-sector writes: ncu counted 2x the ideal L2 store sectors on the 64->32 @512 up layer)
+            float* dst = ep.out_raw_nhwc + pix * Cout + n0 + c;
+            st_global_v8(dst, v[0], v[1], v[2], v[3]);
+            st_global_v8(dst + 8, v[4], v[5], v[6], v[7]);
           } else {
             // o = lrelu(acc * d + noise + bias) * sqrt2: acc*d + noise as one FMA (one rounding less than the reference's
             // separate multiply and add; the tensor-core path is tolerance-checked, 1e-3), then + bias
             const float2 nz2 = make_float2(nz, nz);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 dv = dptr[(c >> 2) + q];
-              v[2 * q] = ffma2(v[2 * q], make_float2(dv.x, dv.y), nz2);
-              v[2 * q + 1] = ffma2(v[2 * q + 1], make_float2(dv.z, dv.w), nz2);
+              v[2 * q] = ffma2(v[2 * q], make_float2(dv[q].x, dv[q].y), nz2);
+              v[2 * q + 1] = ffma2(v[2 * q + 1], make_float2(dv[q].z, dv[q].w), nz2);
               if (act) {
-                const float4 bv = bptr[(c >> 2) + q];
-                v[2 * q] = fadd2(v[2 * q], make_float2(bv.x, bv.y));
-                v[2 * q + 1] = fadd2(v[2 * q + 1], make_float2(bv.z, bv.w));
+                v[2 * q] = fadd2(v[2 * q], make_float2(bv[q].x, bv[q].y));
+                v[2 * q + 1] = fadd2(v[2 * q + 1], make_float2(bv[q].z, bv[q].w));
               }
             }
-            if (act) {
+            if (act && fold_gain) {   // gain already inside d / bias / noise: lrelu = max(x, slope * x)
+              const float2 sl2 = make_float2(ep.slope, ep.slope);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 t = fmul2(v[i], sl2);
+                v[i] = make_float2(fmaxf(v[i].x, t.x), fmaxf(v[i].y, t.y));
+              }
+            } else if (act) {
               const float2 sl2 = make_float2(ep.slope, ep.slope), sc2 = make_float2(ep.act_scale, ep.act_scale);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -456,9 +494,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 h[2 * q] = pack_f16x2_sat(a01.x, a01.y);
                 h[2 * q + 1] = pack_f16x2_sat(a23.x, a23.y);
               }
-              uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(ep.out_hi) + pix * Cout + n0 + c);
-              dh[0] = make_uint4(h[0], h[1], h[2], h[3]);
-              dh[1] = make_uint4(h[4], h[5], h[6], h[7]);
+              // 16 channels x 2 B = one 32-byte sector per pixel: a single 256-bit store
+              st_global_v8_b32(reinterpret_cast<__half*>(ep.out_hi) + pix * Cout + n0 + c, h[0], h[1], h[2], h[3], h[4], h[5],
+                               h[6], h[7]);
             } else if (ep.out_hi) {
               uint32_t h[8], l[8];
 #pragma unroll
@@ -475,12 +513,10 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 l[2 * q] = *reinterpret_cast<const uint32_t*>(&l01);
                 l[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&l23);
               }
-              uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_hi) + pix * Cout + n0 + c);
-              uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out_lo) + pix * Cout + n0 + c);
-              dh[0] = make_uint4(h[0], h[1], h[2], h[3]);
-              dh[1] = make_uint4(h[4], h[5], h[6], h[7]);
-              dl[0] = make_uint4(l[0], l[1], l[2], l[3]);
-              dl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+              st_global_v8_b32(reinterpret_cast<__nv_bfloat16*>(ep.out_hi) + pix * Cout + n0 + c, h[0], h[1], h[2], h[3], h[4],
+                               h[5], h[6], h[7]);
+              st_global_v8_b32(reinterpret_cast<__nv_bfloat16*>(ep.out_lo) + pix * Cout + n0 + c, l[0], l[1], l[2], l[3], l[4],
+                               l[5], l[6], l[7]);
             }
           }
         }

@@ -144,7 +144,7 @@ int maua_synth_prepare(MauaSynth* h, void* plan, size_t plan_bytes, void* stream
       ls.w_hi = base + reinterpret_cast<size_t>(ls.w_hi);
       ls.w_lo = base + reinterpret_cast<size_t>(ls.w_lo);
     }
-    const float scale = 1.0f / std::sqrt((float)(ls.l.cin * 9));
+    const float scale = (float)(1.0 / std::sqrt((double)(ls.l.cin * 9)));   // == Python's 1 / math.sqrt(cin * k * k)
     int rc = maua_weight_sq_f32(ls.l.conv_weight, ls.wsq, ls.l.cout, ls.l.cin, 3, scale, stream);
     if (rc != MAUA_OK) return rc;
     rc = ls.fmt == 2 ? maua_pack_weight_f16x2(ls.l.conv_weight, ls.w_hi, ls.w_lo, ls.l.cout, ls.l.cin, 3, scale, stream)
@@ -286,7 +286,7 @@ int maua_synth_forward(MauaSynth* h, const float* latent, int latent_rows, const
     if (ls.fuse_rgb) {
       partial = reinterpret_cast<float*>(take(px * 3 * 4));
       float* wr = reinterpret_cast<float*>(take((size_t)batch * 3 * l.cout * 4));
-      rc = maua_rgb_weights_f32(l.rgb_weight, ls.rgb_s, wr, batch, l.cout, 1.0f / std::sqrt((float)l.cout), stream);
+      rc = maua_rgb_weights_f32(l.rgb_weight, ls.rgb_s, wr, batch, l.cout, (float)(1.0 / std::sqrt((double)l.cout)), stream);
       if (rc != MAUA_OK) return rc;
       ep.rgb_w = wr; ep.rgb_out = partial;
     }
@@ -298,7 +298,8 @@ int maua_synth_forward(MauaSynth* h, const float* latent, int latent_rows, const
       float* u = reinterpret_cast<float*>(take((size_t)batch * (2 * ls.in_h + 1) * (2 * ls.in_w + 1) * l.cout * 4));
       MauaConvEpilogue er;
       memset(&er, 0, sizeof(er));
-      er.d = ls.d; er.out_raw_nhwc = u; er.activate = 0;
+      er.out_raw_nhwc = u; er.activate = 0;   // raw phases; the demodulation rides in blur_act (commutes with the FIR)
+      ep.d = ls.d;
       er.workspace = ep.workspace; er.workspace_bytes = ep.workspace_bytes;
       rc = maua_modconv_tc(x_hi, x_lo, ls.w_hi, ls.w_lo, &er, batch, l.cin, l.cout, ls.in_h, ls.in_w, 1, ls.fmt, stream);
       if (rc != MAUA_OK) return rc;
@@ -315,7 +316,7 @@ int maua_synth_forward(MauaSynth* h, const float* latent, int latent_rows, const
         rc = maua_rgb_finish_f32(partial, l.rgb_bias, image, upk, dst, batch, ls.out_h, ls.out_w, stream);
       else
         rc = maua_torgb_f32(y, l.rgb_weight, ls.rgb_s, l.rgb_bias, image, upk, dst, batch, l.cout, ls.out_h, ls.out_w,
-                            1.0f / std::sqrt((float)l.cout), stream);
+                            (float)(1.0 / std::sqrt((double)l.cout)), stream);
       if (rc != MAUA_OK) return rc;
       image = dst;
       image_slot ^= 1;

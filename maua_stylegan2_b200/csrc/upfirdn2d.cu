@@ -6,7 +6,9 @@
 //     out = sum_y sum_x in[in0y+y, in0x+x] * K[kh-1-(k0y+y*up), kw-1-(k0x+x*up)]      (y-major, x-minor, fp32 FMA)
 // Every code path below keeps that accumulation order, so results are bit-identical to the reference CUDA op.
 //
-// Two kernels:
+// Three kernels:
+//   blur_tile_pipe_kernel — the default for identity-rate <= 4x4 FIRs on planes wider than 64: persistent CTAs, the global
+//                        loads of tile i+1 in flight while tile i is computed (see the kernel's comment)
 //   blur_tile_kernel   — identity-rate (up=down=1), taps <= 4x4, minor == 1 (Blur after the up-conv: 96 % of the
 //                        upfirdn2d bytes of a frame).  One CTA = one output tile of one plane; the input tile
 //                        (+3 halo) is staged in shared memory with coalesced loads, every thread produces a
@@ -322,21 +324,24 @@ extern "C" int maua_upfirdn2d_f32(const float* x, float* y, const float* k, int 
     dim3 grid(ceil_div(p.out_w, TWV) * ceil_div(p.out_h, TH), planes_y);                     \
     blur_tile_kernel<TWV, RYV, MINBV><<<grid, 256, 0, st>>>(x, y, k, p, vec);                \
   } while (0)
-    if (p.out_w > 64 && variant >= 3) {
-      // software-pipelined persistent kernel (variant 3: 3 CTAs/SM, 4: 4 CTAs/SM, 5: 2 CTAs/SM)
+    if (p.out_w > 64 && (variant == 0 || variant >= 3)) {
+      // software-pipelined persistent kernel.  Measured on B200, [4,32,2049,2049] (4.30 GB in + out, > L2), fraction of the
+      // measured HBM copy peak: one-shot tiles 5 CTAs/SM 0.704 | pipelined 2 CTAs/SM 0.684, 3: 0.722, 4: 0.786 (default)
       constexpr int TH = (256 / (128 / 4)) * 4;
       const long long n_tiles = (long long)ceil_div(p.out_w, 128) * ceil_div(p.out_h, TH) * major;
-      const int per_sm = variant == 4 ? 4 : (variant == 5 ? 2 : 3);
+      const int per_sm = variant == 3 ? 3 : (variant == 5 ? 2 : (variant == 6 ? 5 : (variant == 7 ? 6 : 4)));
       long long g = (long long)device_sm_count() * per_sm;
       if (g > n_tiles) g = n_tiles;
-      if (variant == 4) blur_tile_pipe_kernel<128, 4, 4><<<(unsigned)g, 256, 0, st>>>(x, y, k, p, vec, n_tiles);
-      else if (variant == 5) blur_tile_pipe_kernel<128, 4, 2><<<(unsigned)g, 256, 0, st>>>(x, y, k, p, vec, n_tiles);
-      else blur_tile_pipe_kernel<128, 4, 3><<<(unsigned)g, 256, 0, st>>>(x, y, k, p, vec, n_tiles);
+      if (per_sm == 2) blur_tile_pipe_kernel<128, 4, 2><<<(unsigned)g, 256, 0, st>>>(x, y, k, p, vec, n_tiles);
+      else if (per_sm == 3) blur_tile_pipe_kernel<128, 4, 3><<<(unsigned)g, 256, 0, st>>>(x, y, k, p, vec, n_tiles);
+      else if (per_sm == 5) blur_tile_pipe_kernel<128, 4, 5><<<(unsigned)g, 256, 0, st>>>(x, y, k, p, vec, n_tiles);
+      else if (per_sm == 6) blur_tile_pipe_kernel<128, 4, 6><<<(unsigned)g, 256, 0, st>>>(x, y, k, p, vec, n_tiles);
+      else blur_tile_pipe_kernel<128, 4, 4><<<(unsigned)g, 256, 0, st>>>(x, y, k, p, vec, n_tiles);
     } else if (p.out_w > 64) {
       // measured on B200, [4,32,2049,2049]: (128,4) tiles at 5 CTAs/SM 4.60 TB/s | 4 CTAs 4.24 | (128,8)x2 3.43 |
       // (64,4)x4 3.92 | (128,2)x6 3.93   (MAUA_UFD_VARIANT keeps the alternatives reachable for re-tuning)
-      if (variant == 1) MAUA_BLUR_LAUNCH(128, 4, 4);
-      else if (variant == 2) MAUA_BLUR_LAUNCH(128, 4, 6);
+      // one-shot tile kernel (MAUA_UFD_VARIANT=1: 5 CTAs/SM, 2: 6 CTAs/SM), kept for A/B measurements
+      if (variant == 2) MAUA_BLUR_LAUNCH(128, 4, 6);
       else MAUA_BLUR_LAUNCH(128, 4, 5);
     } else {
       MAUA_BLUR_LAUNCH(32, 2, 4);

@@ -225,8 +225,10 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
                            lp.w_lo.data_ptr(), C.byref(ep), batch, sp.cin, sp.cout, in_h, in_w, 0, nprod, stream)
                 else:
                     u = torch.empty((batch, 2 * in_h + 1, 2 * in_w + 1, sp.cout), device=device, dtype=torch.float32)
+                    # demodulation commutes with the per-channel FIR: the conv streams raw phases, blur_act multiplies by d
                     ep_raw = L.ConvEpilogue()
-                    ep_raw.d, ep_raw.out_raw_nhwc, ep_raw.activate = d.data_ptr(), u.data_ptr(), 0
+                    ep_raw.out_raw_nhwc, ep_raw.activate = u.data_ptr(), 0
+                    ep.d = d.data_ptr()
                     ep_raw.workspace, ep_raw.workspace_bytes = ep.workspace, ep.workspace_bytes
                     L.call("maua_modconv_tc", split[0].data_ptr(), L.ptr(split[1]), lp.w_hi.data_ptr(),
                            lp.w_lo.data_ptr(), C.byref(ep_raw), batch, sp.cin, sp.cout, in_h, in_w, 1, nprod, stream)

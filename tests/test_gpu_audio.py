@@ -180,3 +180,39 @@ def test_madmom_flavoured_onsets_vs_oracle():
         assert np.abs(got - ref).max() < 2e-2, kw
     with pytest.raises(ValueError):
         S.onsets(y, SR, n_frames, type="nope")
+
+
+def test_laplacian_segmentation_finds_section_changes():
+    """audioreactive.laplacian_segmentation (signal.py:159-240 of the reference; librosa absent -> restated, parity unpinned):
+    three 20 s sections with different chords over a 120 BPM click must come back as segments whose boundaries sit
+    within two beats of the true changes, with the A sections sharing a label that differs from the B section."""
+    from maua_stylegan2_b200 import audioreactive as ar
+
+    sr, sec = 22050, 20
+    t = np.arange(sr * sec) / sr
+    rng = np.random.default_rng(0)
+
+    def chord(freqs):
+        y = sum(np.sin(2 * np.pi * f * t) / (1 + i) for i, f in enumerate(freqs))
+        return y / np.abs(y).max()
+
+    a, b = chord([220.0, 277.18, 329.63, 440.0]), chord([174.61, 233.08, 349.23, 698.46])
+    y = np.concatenate([a, b, a]).astype(np.float32) * 0.5
+    click = np.zeros_like(y)
+    for n in range(0, len(y), sr // 2):                       # 120 BPM
+        click[n:n + 200] += np.hanning(200) * 0.8
+    y = y + click + 0.01 * rng.standard_normal(len(y)).astype(np.float32)
+    times, labels = ar.laplacian_segmentation(y, sr, k=2)
+    print("segments", [round(x, 2) for x in times], labels)
+    assert times[0] == 0.0 and len(times) == len(labels) >= 3
+    assert all(t1 > t0 for t0, t1 in zip(times, times[1:]))
+    for true_t in (20.0, 40.0):
+        assert min(abs(x - true_t) for x in times) <= 1.5, (true_t, times)
+
+    def label_at(sec_):
+        return labels[max(i for i, x in enumerate(times) if x <= sec_)]
+
+    assert label_at(10.0) == label_at(50.0) != label_at(30.0)
+    # determinism (k-means is seeded)
+    times2, labels2 = ar.laplacian_segmentation(y, sr, k=2)
+    assert times2 == times and labels2 == labels

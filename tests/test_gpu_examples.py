@@ -108,3 +108,9 @@ def test_kelp_hooks_perlin_loops():
     assert all(bool(torch.isfinite(n).all()) for n in noise)   # (perlin * 2 - 1 is not confined to [-1, 1], as in the reference)
     frames = _render(g, lat[:16].contiguous(), [n[:16].contiguous() for n in noise], hooks.get_bends(args), 8)
     assert frames.shape == (16, 64, 128, 3)
+    # without caller-supplied sections the hook segments the track itself, like the reference (ar.laplacian_segmentation)
+    args.sections = None
+    stamps, labels = hooks.sections(args)
+    assert stamps[0] == 0.0 and stamps[-1] == args.duration and len(labels) == len(stamps) - 1
+    lat2 = hooks.get_latents(sel, args)
+    assert tuple(lat2.shape) == (120, g.n_latent, 512) and bool(torch.isfinite(lat2).all())

@@ -19,7 +19,7 @@ def _pack(w, scale, fmt="bf16x3"):
     return _pack_tc(w[None].contiguous(), scale, fmt)
 
 
-def _run_tc(x, w, s, d, noise, nw, bias, s_next, up, nprod, scale, workspace=None, out_f16=False):
+def _run_tc(x, w, s, d, noise, nw, bias, s_next, up, nprod, scale, workspace=None, out_f16=False, d_in_conv=False):
     """nprod 3 / 1: bf16 (hi, lo) activations; nprod 2: the "f16" format (one fp16 activation plane, fp16 weight pair).
     out_f16: the epilogue writes the consumer's activations as one fp16 plane (returned as o_hi, o_lo = zeros)."""
     from maua_stylegan2_b200 import _lib as L
@@ -54,7 +54,11 @@ def _run_tc(x, w, s, d, noise, nw, bias, s_next, up, nprod, scale, workspace=Non
     else:
         u = torch.full((b, 2 * h + 1, 2 * wd + 1, cout), float("nan"), device="cuda")
         er = L.ConvEpilogue()
-        er.d, er.out_raw_nhwc, er.activate = d.data_ptr(), u.data_ptr(), 0
+        er.out_raw_nhwc, er.activate = u.data_ptr(), 0
+        if d_in_conv:      # stand-alone form: the conv epilogue applies the demodulation itself
+            er.d = d.data_ptr()
+        else:              # product form: raw phases out of the conv, d applied by blur_act (commutes with the FIR)
+            ep.d = d.data_ptr()
         er.workspace, er.workspace_bytes = ep.workspace, ep.workspace_bytes
         L.call("maua_modconv_tc", hi.data_ptr(), lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), C.byref(er), b, cin,
                cout, h, wd, 1, nprod, stream)
@@ -73,7 +77,7 @@ def _reference(x, w, s, d, noise, nw, bias, up, scale):
         raw = None
     else:
         o = F.conv_transpose2d(xs, (w * scale).transpose(0, 1), stride=2)     # [B,Cout,2H+1,2W+1]
-        raw = (o * d[:, :, None, None]).permute(0, 2, 3, 1)
+        raw = o.permute(0, 2, 3, 1)                                           # raw phases (no demodulation)
         k = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=torch.float64)
         k4 = (k[None] * k[:, None] / 16)
         c = o.shape[1]
@@ -275,6 +279,17 @@ def test_f16_layout_kernels():
     wantw = (w[0] * 0.25).permute(2, 3, 0, 1).reshape(9, 24, 40)
     assert w_hi.dtype == torch.float16 and torch.equal(w_hi, wantw.to(torch.float16))
     assert (w_hi.float() + w_lo.float() - wantw).abs().max() <= wantw.abs().max() * 2 ** -20
+
+
+def test_up_conv_with_demodulation_in_the_conv_epilogue():
+    """Stand-alone form of the transposed conv: ep.d given to the conv (u = d * convT(x)), none to blur_act."""
+    for case in ((2, 64, 32, 72, 40, True), (8, 512, 512, 4, 4, True)):
+        b, cin, cout, h, w, up = case
+        x, wt, s, d, noise, nw, bias, s_next, scale = _case_tensors(b, cin, cout, h, w, up, 900 + cin)
+        ref, raw = _reference(x, wt, s, d, noise, nw, bias, up, scale)
+        y, o_hi, o_lo, u = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 3, scale, d_in_conv=True)
+        assert rel_err(u.cpu().numpy(), (raw * d.double().cpu()[:, None, None, :]).numpy()) < 2e-4
+        assert rel_err(y.cpu().numpy(), ref.numpy()) < 2e-4
 
 
 def test_tc2_fused_torgb_partial_sums():
