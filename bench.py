@@ -259,6 +259,7 @@ def main():
     ap.add_argument("--precision", default=DEFAULT_PRECISION, choices=["bf16x3", "mixed", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-audio-chain", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -288,7 +289,7 @@ def main():
     import torch.distributed as dist
 
     from maua_stylegan2_b200 import _lib as L
-    from maua_stylegan2_b200.parallel import AllGatherFrames, init_from_env
+    from maua_stylegan2_b200.parallel import AllGatherFrames, HostFrameRing, init_from_env, ring_name
     from maua_stylegan2_b200.render import FramePipeline
 
     rank, world, local_rank = init_from_env()
@@ -323,7 +324,12 @@ def main():
         idx = torch.tensor([j % n_frames for j in range(lo, lo + n_steps * B * world)]).to(lat.device)
         pipe = FramePipeline(g, lat[idx], [x[idx] if x is not None else None for x in nz], B, truncation=1.0, rank=rank,
                              world=world)
-        if to_host and rank == 0:
+        ring = None
+        if to_host and world > 1:
+            # every rank copies ITS frames device->host into a shared pinned ring over its own PCIe link; rank 0's sink
+            # reads world*B consecutive frames per step from host memory (render.render does the same)
+            ring = HostFrameRing(f"{ring_name()}_{offset}_{n_steps}", rank, world, B, (SIZE, SIZE, 3))
+        elif to_host:
             pipe.prepare_host_buffers((SIZE, SIZE, 3))
         pipe.warmup()
         sink_bytes = [0]
@@ -336,11 +342,14 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        pipe.run(consume if (to_host and rank == 0) else None, gather)
+        pipe.run(consume if (to_host and rank == 0) else None, gather, ring)
         e1.record()      # (run() makes the compute stream wait for the last collectives before returning)
         torch.cuda.synchronize()
         barrier()
-        return e0.elapsed_time(e1), time.perf_counter() - t0, pipe
+        wall = time.perf_counter() - t0
+        if ring is not None:
+            ring.close()
+        return e0.elapsed_time(e1), wall, pipe
 
     with torch.no_grad():
         sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -362,18 +371,25 @@ def main():
         pipeline_run(latents_h, noise_h, args.warmup, 0, True)
         _, dt, pipe = pipeline_run(latents_h, noise_h, args.steps, args.warmup, True)
         dtt = torch.tensor([dt], device=device)
+        traffic = torch.tensor([float(pipe.h2d_bytes), float(pipe.d2h_bytes)], device=device)
         if world > 1:
             dist.all_reduce(dtt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(traffic, op=dist.ReduceOp.SUM)
         e2e = {"value": args.steps * B * world / float(dtt.item()), "unit": "frames/s",
-               "h2d_bytes_per_step": pipe.h2d_bytes // args.steps, "d2h_bytes_per_step": pipe.d2h_bytes // max(args.steps, 1),
-               "api": "maua_stylegan2_b200.render.FramePipeline (pinned host latents/noise -> uint8 frames in pinned host memory)"}
+               "h2d_bytes_per_step": int(traffic[0].item()) // args.steps,
+               "d2h_bytes_per_step": int(traffic[1].item()) // max(args.steps, 1),
+               "api": "maua_stylegan2_b200.render.FramePipeline (pinned host latents/noise -> uint8 frames in pinned host memory)"
+                      + ("; bytes summed over ranks: every rank uploads its own batches and copies its own frames into a "
+                         "shared pinned host ring (parallel.HostFrameRing) read by rank 0's sink" if world > 1 else "")}
 
         # ---- roofline pass: CUDA events around every launch of the hot kernels (rank 0, a few extra steps) --------
         roof = roof_ufd = shares = None
         if rank == 0:
-            names = {"maua_modconv_tc", "maua_modconv_simt_f32", "maua_blur_act_nhwc", "maua_torgb_f32",
+            names = {"maua_modconv_tc", "maua_modconv_simt_f32", "maua_blur_act_nhwc", "maua_torgb_f32", "maua_rgb_finish_u8",
                      "maua_modulate_split_nhwc", "maua_style_prologue_f32", "maua_rgb_to_u8_nhwc", "maua_upfirdn2d_f32",
                      "maua_noise_bias_act_f32", "maua_rgb_finish_f32", "maua_rgb_weights_f32"}
+            step_local(999)    # un-instrumented warm-up of the per-operator path (plan build, first-use attribute calls)
+            torch.cuda.synchronize()
             L.PROFILE = {"names": names, "events": []}
             nprof = 3
             for i in range(nprof):
@@ -381,20 +397,26 @@ def main():
             torch.cuda.synchronize()
             ev = L.PROFILE["events"]
             L.PROFILE = None
+            # the k-th launch of every instrumented step is the same kernel on the same shapes: take the MEDIAN over the
+            # steps (a host-side hiccup between the start event and the launch — e.g. a Python GC pause — lands inside
+            # one launch's event pair and would otherwise inflate that layer's mean)
+            per_step = len(ev) // nprof
+            times = [statistics.median(ev[k + j * per_step][2].elapsed_time(ev[k + j * per_step][3]) for j in range(nprof))
+                     for k in range(per_step)]
             tot = {}
             conv_ms, conv_fl, conv_issued = 0.0, 0.0, 0.0
             per_layer = {}
-            for name, tag, s, e in ev:
-                t = s.elapsed_time(e)
-                tot[name] = tot.get(name, 0.0) + t / nprof
+            for (name, tag, _, _), t in zip(ev[:per_step], times):
+                tot[name] = tot.get(name, 0.0) + t
+                t *= nprof   # (the sums below are divided by nprof)
                 if name in ("maua_modconv_tc", "maua_modconv_simt_f32") and tag is not None:
                     conv_ms += t
-                    conv_fl += tag["flops"]
-                    conv_issued += tag["flops"] * tag.get("nprod", 1)
+                    conv_fl += tag["flops"] * nprof
+                    conv_issued += tag["flops"] * tag.get("nprod", 1) * nprof
                     key = f"L{tag['layer']}:{tag['cin']}->{tag['cout']}@{tag['h']}{'up' if tag['up'] else ''}"
                     a = per_layer.setdefault(key, [0.0, 0.0])
                     a[0] += t
-                    a[1] += tag["flops"]
+                    a[1] += tag["flops"] * nprof
             shares = {k: round(v, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}
             if conv_ms > 0:
                 ach = conv_fl / (conv_ms * 1e-3) / 1e12
@@ -457,6 +479,18 @@ def main():
         except Exception as e:  # oracle/_ref absent: say so instead of inventing a number
             gpu_ref = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
+    # ---- audio chain: the default hooks of generate() on configs[1]'s 30 s of synthetic audio —
+    # device ms per hook next to the numpy restatement on the host (bounded sample for the noise maps, stated in the keys)
+    audio_chain = None
+    if rank == 0 and world == 1 and not args.no_audio_chain:
+        try:
+            from tools import bench_audio
+
+            torch.cuda.empty_cache()
+            audio_chain = bench_audio.measure(AUDIO_S, oracle=not args.no_cpu_baseline)
+        except Exception as e:
+            audio_chain = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_port_run(steps=2, warmup=1, budget_s=40.0)
@@ -470,7 +504,7 @@ def main():
                 "dtype": DTYPES[args.precision] if args.conv == "tc" else "f32",
                 "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(lt.item()), "roofline": roof, "roofline_upfirdn2d": roof_ufd,
-                "kernel_ms_per_step": shares, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
+                "kernel_ms_per_step": shares, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "audio_chain": audio_chain,
                 "conv_gflop_per_frame": CONV_GFLOP_PER_FRAME}
         _emit(line)
     if world > 1:

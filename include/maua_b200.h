@@ -145,6 +145,11 @@ int maua_rgb_weights_f32(const float* wrgb, const float* s, float* wr, int batch
 int maua_rgb_finish_f32(const float* partial, const float* bias, const float* skip, const float* k4, float* y,
                         int batch, int h, int w, void* stream);
 
+/* maua_rgb_finish_f32 followed by maua_rgb_to_u8_nhwc in one pass (the last ToRGB of a frame when only bytes are wanted):
+ * out[b,y,x,k] = u8( (partial[b,k] + bias[k]) + up2(skip)[b,k] ); w % 4 == 0.  The fp32 image is never materialised. */
+int maua_rgb_finish_u8(const float* partial, const float* bias, const float* skip, const float* k4, uint8_t* out, int batch,
+                       int h, int w, void* stream);
+
 /* out[b,y,x,c] = (uint8) trunc( (clamp(rgb[b,c,y,x], -1, 1) + 1) * 127.5 ) */
 int maua_rgb_to_u8_nhwc(const float* rgb, uint8_t* out, int batch, int h, int w, void* stream);
 

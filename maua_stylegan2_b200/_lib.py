@@ -6,7 +6,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmaua_b200.so")
+LIB_PATH = os.environ.get("MAUA_LIB_PATH") or os.path.join(_PKG, "libmaua_b200.so")   # MAUA_LIB_PATH: A/B builds (tools/)
 
 
 class MauaError(RuntimeError):
@@ -59,6 +59,7 @@ SIGNATURES = {
     "maua_rgb_to_u8_nhwc": [_p, _p, _i, _i, _i, _p],
     "maua_rgb_weights_f32": [_p, _p, _p, _i, _i, _f, _p],
     "maua_rgb_finish_f32": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "maua_rgb_finish_u8": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "maua_pack_weight_bf16x2": [_p, _p, _p, _i, _i, _i, _f, _p],
     "maua_pack_weight_f16x2": [_p, _p, _p, _i, _i, _i, _f, _p],
     "maua_modulate_split_nhwc": [_p, _ll, _p, _p, _p, _i, _i, _i, _i, _p],

@@ -38,7 +38,15 @@ def _newest_header():
     return t
 
 
-def build(verbose=False, force=False):
+def build(verbose=False, force=False, extra_flags=(), tag=""):
+    """tag / extra_flags: an experimental variant (e.g. tag="epi4", extra_flags=["-DMAUA_EPI_GROUPS=4"]) is built into
+    build_<tag>/ and libmaua_b200_<tag>.so; MAUA_LIB_PATH selects it at run time (tools/ A/B measurements)."""
+    global OBJ, LIB
+    obj_dir, lib_path = (OBJ, LIB) if not tag else (os.path.join(PKG, f"build_{tag}"), os.path.join(PKG, f"libmaua_b200_{tag}.so"))
+    return _build(verbose, force, list(extra_flags), obj_dir, lib_path)
+
+
+def _build(verbose, force, extra_flags, OBJ, LIB):
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
@@ -54,7 +62,7 @@ def build(verbose=False, force=False):
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc] + NVCC_FLAGS + ["-Xptxas", "-v" if verbose else "-warn-spills", "-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra_flags + ["-Xptxas", "-v" if verbose else "-warn-spills", "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, r.returncode, r.stdout + r.stderr
 
@@ -76,4 +84,6 @@ def build(verbose=False, force=False):
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    tag = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--tag=")), "")
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, extra_flags=extra, tag=tag))

@@ -34,7 +34,10 @@ constexpr int TH = 16, TW = 8;  // one M tile = 16 rows x 8 columns
 #define MAUA_EPI_GROUPS 3
 #endif
 constexpr int EPI_GROUPS = MAUA_EPI_GROUPS;
-constexpr int ROLE_WARPS = EPI_GROUPS >= 4 ? 4 : 2;   // warps before the first epilogue warp
+#ifndef MAUA_ROLE_WARPS
+#define MAUA_ROLE_WARPS (MAUA_EPI_GROUPS >= 4 ? 4 : 2)
+#endif
+constexpr int ROLE_WARPS = MAUA_ROLE_WARPS;   // warps before the first epilogue warp (4: a warpgroup of their own -> setmaxnreg)
 constexpr int THREADS = 32 * ROLE_WARPS + 128 * EPI_GROUPS;
 
 struct Params {
@@ -56,6 +59,10 @@ struct Params {
   int n_phase;           // accumulator phases per item: 1 same-res; transposed: 4 / 2 / 1 (4 / n_groups)
   int n_groups;          // transposed only: phase groups walked as separate work items (1, 2 or 4)
   int n_items;           // work items = n_tiles * tiles_x * tiles_y * B, walked with stride gridDim.x
+  // exact division of item indices by runtime constants without the ~35-instruction integer-division sequences (every
+  // role warp decodes every item: 160 of the ~1000 epilogue instructions per item were these, ncu source view)
+  uint32_t fd_m[4], fd_s[4];   // 0: per_group, 1: n_tiles, 2: tiles_x, 3: tiles_y   q = (umulhi(x, m) + x) >> s, x < 2^31
+  int per_group;
   int dbg;               // MAUA_TC_DBG (timing experiments, results invalid): 1 = empty epilogue, 2 = no A loads after the
                          // first, 4 = epilogue stops after the TMEM loads, 8 = epilogue without TMEM loads
 };
@@ -135,15 +142,24 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 
   // work item -> (phase group, pixel tile, n tile); n fastest (concurrently running CTAs share the halo through L2),
   // group slowest (load balance: the groups have 5/4 or 4/2/2/1 taps)
+  auto fdiv = [&](int x, int which) -> int {
+    return (int)((__umulhi((uint32_t)x, p.fd_m[which]) + (uint32_t)x) >> p.fd_s[which]);
+  };
   auto decode = [&](int item, int& n0, int& grp, int& x0, int& y0, int& b) {
-    const int per_group = p.n_items / p.n_groups;
-    grp = item / per_group;
-    item -= grp * per_group;
-    const int n_tile = item % p.n_tiles;
-    const int rest = item / p.n_tiles;
-    x0 = (rest % p.tiles_x) * TW;
-    y0 = ((rest / p.tiles_x) % p.tiles_y) * TH * p.R;
-    b = rest / (p.tiles_x * p.tiles_y);
+    grp = 0;
+    if (UP && p.n_groups > 1) {
+      grp = fdiv(item, 0);
+      item -= grp * p.per_group;
+    }
+    int rest = item, n_tile = 0;
+    if (p.n_tiles > 1) {
+      rest = fdiv(item, 1);
+      n_tile = item - rest * p.n_tiles;
+    }
+    const int q1 = fdiv(rest, 2);            // rest / tiles_x
+    x0 = (rest - q1 * p.tiles_x) * TW;
+    b = fdiv(q1, 3);                         // q1 / tiles_y
+    y0 = (q1 - b * p.tiles_y) * TH * p.R;
     n0 = n_tile * p.BN;
   };
   auto tap_list = [&](int grp) -> const TapList& {
@@ -153,7 +169,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const uint32_t acc_cols = (uint32_t)(p.n_phase * p.R) * blk_cols;  // ... of one accumulator stage
   const uint32_t halo_bytes = (uint32_t)(p.HW_ * p.HH_) * ROW;    // bytes one TMA box writes per plane
 
-  if (EPI_GROUPS >= 4) {  // register hand-over between warpgroups (all warps of a warpgroup execute the same instruction)
+  if (ROLE_WARPS >= 4) {  // register hand-over between warpgroups (all warps of a warpgroup execute the same instruction)
     if (warp < ROLE_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
   }
@@ -639,9 +655,15 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     else if (cout == 128) { pr = up ? 1 : 2; pbn = 128; pg = up ? 2 : 1; }
     else if (cout == 64) { pr = up ? 2 : 1; pbn = 64; pg = up ? 2 : 1; pcat = up ? 0 : 1; }
     else { pr = up ? 1 : 4; pbn = cout; pcat = 1; }
-    if (n_products == 2 && cout <= 64) {  // fp16: the concat MMA is the whole product -> always for BN <= 64
-      pcat = 1;
-      if (cout == 64) { pr = up ? 1 : 2; pg = up ? 2 : 1; }
+    if (n_products == 2 && cout <= 64) {
+      // fp16 (tools/tune_tc2.py --prod 2, batch 8): same-res layers take the concat MMA (one N = 2*BN MMA per K-step:
+      // 64->64 @512 R=2 0.258 ms vs 0.304 without; 32->32 @1024 R=4 0.434 vs 0.556); the transposed layers are paced by
+      // their epilogue's HBM stores, where the concat's second TMEM load + add per chunk costs more than the MMAs it
+      // saves (128->64 @256 up: R=2, 2 groups, no concat 0.228 ms vs 0.259; 64->32 @512 up: R=2 no concat 0.301 vs 0.335)
+      pcat = up ? 0 : 1;
+      pr = 2;
+      if (cout == 64) pg = up ? 2 : 1;
+      else { pr = up ? 2 : 4; pg = 1; }
     }
     if (force_groups && up) pg = force_groups;
     while (pr > 1 && pr > rows16) pr >>= 1;
@@ -690,6 +712,16 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   const long long items = tiles_x * p.tiles_y * batch * p.n_tiles * p.n_groups;
   if (items >= (1LL << 31)) return MAUA_E_UNSUPPORTED;
   p.n_items = (int)items;
+  p.per_group = (int)(items / p.n_groups);
+  {
+    const uint32_t ds[4] = {(uint32_t)p.per_group, (uint32_t)p.n_tiles, (uint32_t)p.tiles_x, (uint32_t)p.tiles_y};
+    for (int i = 0; i < 4; ++i) {
+      uint32_t sh = 0;
+      while ((1ull << sh) < ds[i]) ++sh;
+      p.fd_s[i] = sh;
+      p.fd_m[i] = (uint32_t)((((1ull << sh) - ds[i]) << 32) / ds[i] + 1);
+    }
+  }
   p.AS = (2 * blk_cols * R * p.n_phase <= 512) ? 2 : 1;
   static const int dbg = [] { const char* e = getenv("MAUA_TC_DBG"); return e ? atoi(e) : 0; }();
   p.dbg = dbg;

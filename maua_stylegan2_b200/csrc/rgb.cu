@@ -188,6 +188,45 @@ __global__ void __launch_bounds__(256) rgb_finish_kernel(const float* __restrict
   }
 }
 
+// Last ToRGB of a frame straight to bytes: (partial + bias) + up2(skip) for the three planes of 4 consecutive pixels, then
+// render.py:40-43's clamp / scale / truncate and the NCHW -> NHWC interleave — 12 bytes out per thread.  The fp32 image of
+// the final resolution (100 MB per batch of 8 at 1024^2) is never written or re-read.  Same rounding as
+// rgb_finish_kernel followed by rgb_to_u8_kernel.
+__global__ void __launch_bounds__(256) rgb_finish_u8_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
+                                                            const float* __restrict__ skip, const float* __restrict__ k4,
+                                                            uint8_t* __restrict__ out, int h, int w, long long total_vec) {
+  __shared__ float kf[16];
+  if (threadIdx.x < 16) kf[threadIdx.x] = k4 ? __ldg(k4 + threadIdx.x) : 0.f;
+  __syncthreads();
+  const int wv = w / 4;
+  const long long hwv = (long long)h * wv, hw = (long long)h * w;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total_vec; i += (long long)gridDim.x * 256) {
+    const long long b = i / hwv;
+    const int rem = (int)(i - b * hwv);
+    const int oy = rem / wv, ox0 = (rem - oy * wv) * 4;
+    uint8_t px[12];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(partial + (b * 3 + k) * hw + (long long)oy * w + ox0));
+      float o[4] = {t.x, t.y, t.z, t.w};
+      const float bb = bias ? __ldg(bias + k) : 0.f;
+      const float* sp = skip ? skip + (b * 3 + k) * (h >> 1) * (w >> 1) : nullptr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = __fadd_rn(o[j], bb);
+        if (skip) v = __fadd_rn(v, skip_up2(sp, h >> 1, w >> 1, kf, oy, ox0 + j));
+        v = fminf(fmaxf(v, -1.f), 1.f);
+        v = __fmul_rn(__fadd_rn(v, 1.f), 127.5f);
+        px[j * 3 + k] = (uint8_t)(int)v;
+      }
+    }
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + ((b * h + oy) * (long long)w + ox0) * 3);   // 12-byte aligned: ox0 % 4 == 0
+    dst[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
+    dst[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
+    dst[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
+  }
+}
+
 // one thread = one pixel (3 planar loads coalesced across the warp, 3 packed bytes out)
 __global__ void __launch_bounds__(256) rgb_to_u8_kernel(const float* __restrict__ rgb, uint8_t* __restrict__ out,
                                                         long long hw, long long total) {
@@ -279,7 +318,7 @@ extern "C" int maua_torgb_f32(const float* x, const float* wrgb, const float* s,
   const size_t smem = 3 * (size_t)cin * sizeof(float);
   const bool vec = (hw % 4 == 0) && (w % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
-  if (hw <= 4096 && cin >= 64) {
+  if (hw <= 16384 && cin >= 64) {  // channel-split kernel: the serial-channel kernel ran the 256-ch 128^2 ToRGB at 22 % DRAM
     dim3 grid((unsigned)ceil_div(hw, 32LL), batch);
     torgb_small_kernel<<<grid, 256, smem, st>>>(x, wrgb, s, bias, skip, k4, y, cin, h, w, w_scale);
   } else if (vec) {
@@ -330,5 +369,21 @@ extern "C" int maua_rgb_finish_f32(const float* partial, const float* bias, cons
   if (vec) rgb_finish_kernel<4><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(partial, bias, skip, k4, y, h, w, work);
   else rgb_finish_kernel<1><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(partial, bias, skip, k4, y, h, w, work);
   MAUA_CHECK_LAUNCH("rgb_finish");
+  return MAUA_OK;
+}
+
+extern "C" int maua_rgb_finish_u8(const float* partial, const float* bias, const float* skip, const float* k4, uint8_t* out,
+                                  int batch, int h, int w, void* stream) {
+  using namespace maua;
+  MAUA_CHECK_ARG(partial && out && batch >= 0 && h >= 1 && w >= 1, "rgb_finish_u8: bad arguments");
+  MAUA_CHECK_ARG(!skip || (k4 && (h % 2 == 0) && (w % 2 == 0)), "rgb_finish_u8: skip needs k4 and even output size");
+  MAUA_CHECK_ARG(w % 4 == 0 && (reinterpret_cast<uintptr_t>(partial) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0,
+                 "rgb_finish_u8: width must be a multiple of 4 and the buffers 16 / 4 byte aligned");
+  const long long work = (long long)batch * h * (w / 4);
+  if (work == 0) return MAUA_OK;
+  long long blocks = ceil_div(work, 256LL);
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  rgb_finish_u8_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(partial, bias, skip, k4, out, h, w, work);
+  MAUA_CHECK_LAUNCH("rgb_finish_u8");
   return MAUA_OK;
 }

@@ -312,7 +312,10 @@ int maua_synth_forward(MauaSynth* h, const float* latent, int latent_rows, const
       float* dst = (last_rgb && out_rgb) ? out_rgb : h->image[image_slot];
       const float* upk = image ? l.rgb_up_kernel : nullptr;
       MAUA_CHECK_ARG(!image || upk, "synth_forward: layer %d needs rgb_up_kernel for its skip connection", (int)li);
-      if (ls.fuse_rgb)
+      const bool bytes_only = last_rgb && out_u8 && !out_rgb && ls.fuse_rgb && ls.out_w % 4 == 0;
+      if (bytes_only)   // last ToRGB straight to uint8 NHWC: the full-resolution fp32 image is never written
+        rc = maua_rgb_finish_u8(partial, l.rgb_bias, image, upk, out_u8, batch, ls.out_h, ls.out_w, stream);
+      else if (ls.fuse_rgb)
         rc = maua_rgb_finish_f32(partial, l.rgb_bias, image, upk, dst, batch, ls.out_h, ls.out_w, stream);
       else
         rc = maua_torgb_f32(y, l.rgb_weight, ls.rgb_s, l.rgb_bias, image, upk, dst, batch, l.cout, ls.out_h, ls.out_w,
@@ -320,7 +323,7 @@ int maua_synth_forward(MauaSynth* h, const float* latent, int latent_rows, const
       if (rc != MAUA_OK) return rc;
       image = dst;
       image_slot ^= 1;
-      if (last_rgb && out_u8) {
+      if (last_rgb && out_u8 && !bytes_only) {
         rc = maua_rgb_to_u8_nhwc(image, out_u8, batch, ls.out_h, ls.out_w, stream);
         if (rc != MAUA_OK) return rc;
       }

@@ -253,7 +253,15 @@ def synthesize(g, latent, noise, truncation, bends, want_acts=False, want_u8=Fal
             if want_acts:
                 acts.append(x)
             current_size *= 2 if (sp.up or li == 0) else 1
-            if sp.rgb is not None and lp.tc_ok and rgb_partial is not None:
+            last_rgb = sp.rgb is not None and not any(l2.spec.rgb is not None for l2 in layers[li + 1:])
+            if sp.rgb is not None and lp.tc_ok and rgb_partial is not None and want_u8 and last_rgb and out_w % 4 == 0:
+                # last ToRGB straight to uint8 NHWC (the full-resolution fp32 image is never written)
+                u8 = torch.empty((batch, out_h, out_w, 3), device=device, dtype=torch.uint8)
+                L.call("maua_rgb_finish_u8", rgb_partial.data_ptr(), sp.rgb.bias.data_ptr(), L.ptr(image),
+                       sp.rgb.upsample.kernel.data_ptr() if image is not None else None, u8.data_ptr(), batch, out_h,
+                       out_w, stream)
+                image, want_u8 = u8, False
+            elif sp.rgb is not None and lp.tc_ok and rgb_partial is not None:
                 new_image = torch.empty_like(rgb_partial)
                 L.call("maua_rgb_finish_f32", rgb_partial.data_ptr(), sp.rgb.bias.data_ptr(), L.ptr(image),
                        sp.rgb.upsample.kernel.data_ptr() if image is not None else None, new_image.data_ptr(), batch,

@@ -253,3 +253,21 @@ def test_generator_512_confige_bend_and_truncation_sweep():
     assert img.shape == (b, 3, 512, 512)
     errs = [rel_err(a.cpu().numpy(), r.numpy()) for a, r in zip(acts, ref_acts)]
     assert max(errs) < TOL["tc"] and rel_err(img.cpu().numpy(), ref_img.numpy()) < TOL["tc"]
+
+
+@pytest.mark.parametrize("size,cm", [(256, 1), (512, 1)])
+def test_return_u8_equals_u8_of_the_fp32_image(size, cm):
+    """`return_u8=True` ends in maua_rgb_finish_u8 (last ToRGB + bias + skip + clamp/scale/truncate in one pass, no fp32
+    image): the bytes must equal the two-step path (fp32 image -> maua_rgb_to_u8_nhwc) and render.py:40-43's arithmetic."""
+    from maua_stylegan2_b200.stylegan2 import frames_to_u8
+
+    g, _ = make_generator(size, cm, 12, "tc")
+    g.truncation_latent = torch.zeros(1, 512, device="cuda")
+    gen = torch.Generator().manual_seed(3)
+    latent = (torch.randn(3, g.n_latent, 512, generator=gen) * 0.6).cuda()
+    with torch.no_grad():
+        img, _ = g(latent, truncation=0.9, input_is_latent=True, randomize_noise=False)
+        u8, _ = g(latent, truncation=0.9, input_is_latent=True, randomize_noise=False, return_u8=True)
+    assert u8.dtype == torch.uint8 and tuple(u8.shape) == (3, size, size, 3)
+    assert torch.equal(u8, frames_to_u8(img))
+    assert np.array_equal(u8.cpu().numpy(), O.frames_to_u8(img.cpu()))
