@@ -355,13 +355,16 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       // Noise of this lane's pixel in each of the item's R tiles, requested BEFORE waiting for the accumulators: the
       // noise map is streamed from HBM/L2 (4 B per pixel, no reuse), and with the load next to its use its ~1 us latency
       // was the largest single stall of the same-resolution epilogue (ncu: 21 % of its samples on the consuming FMUL).
+      // (with fused ToRGB a warp owns whole tiles — first_job and first_job + EPI_GROUPS — and only needs their values)
+      const int first_job_rgb = (egroup + EPI_GROUPS - job0) % EPI_GROUPS;
       float nzv[4] = {0.f, 0.f, 0.f, 0.f};
       if (!UP && act && ep.noise) {
         const float* nrow = ep.noise + (long long)b * ep.noise_bstride + gx;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const int gy = y0 + r * TH + ty;
-          if (r < R && gy < GH && gx < GW) nzv[r] = __ldg(nrow + (long long)gy * OW);
+          const bool mine = !fuse_rgb || r == first_job_rgb || r == first_job_rgb + EPI_GROUPS;
+          if (mine && r < R && gy < GH && gx < GW) nzv[r] = __ldg(nrow + (long long)gy * OW);
         }
       }
       mbar_wait(acc_full + 8 * as, pacc);
@@ -374,7 +377,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const float4* bptr = reinterpret_cast<const float4*>(sm_b + n0);
       const float4* sptr = reinterpret_cast<const float4*>(sm_s + n0);
       const int njobs = (p.dbg & 1) ? 0 : (fuse_rgb ? R : ntile * nchunk);
-      const int first_job = fuse_rgb ? (egroup + EPI_GROUPS - job0) % EPI_GROUPS : egroup;
+      const int first_job = fuse_rgb ? first_job_rgb : egroup;
 #pragma unroll 1
       for (int job = first_job; job < njobs; job += EPI_GROUPS) {
         const int tile = fuse_rgb ? job : (job >> bn16_log);   // accumulator index = ph * R + r

@@ -73,6 +73,16 @@ def current():
     return 0, 1
 
 
+def all_ranks_agree(flag, device=None):
+    """Logical AND of a per-rank boolean over the default process group (every rank gets the same answer)."""
+    if current()[1] == 1:
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32,
+                     device=device if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
 def broadcast_inputs(tensors, src=0, device=None):
     """Make per-frame inputs identical on every rank (hooks draw random noise: each rank would otherwise filter its own
     random stream and consecutive batches, rendered by different ranks, would not be temporally coherent).
@@ -110,6 +120,18 @@ class HostFrameRing:
     publishes ready[r] = i+1 once its D2H event has completed; rank 0 waits for every ready[r] >= i+1."""
 
     HEADER = 4096
+    DIR = os.environ.get("MAUA_RING_DIR", "/dev/shm")
+
+    @classmethod
+    def fits(cls, world, batch, frame_shape):
+        """True when the shared-memory file system has room for the ring (containers often cap /dev/shm at 64 MB; writing
+        past the cap raises SIGBUS, so callers fall back to gather-then-D2H on rank 0 instead of trying)."""
+        need = cls.HEADER + 2 * world * batch * int(torch.tensor(frame_shape).prod()) + (16 << 20)
+        try:
+            st = os.statvfs(cls.DIR)
+            return st.f_bavail * st.f_frsize >= need
+        except OSError:
+            return False
 
     def __init__(self, name, rank, world, batch, frame_shape, timeout_s=180.0):
         import numpy as np
@@ -118,7 +140,7 @@ class HostFrameRing:
         self.frame_shape = tuple(frame_shape)
         self.shard_bytes = batch * int(np.prod(self.frame_shape))
         self.nbytes = self.HEADER + 2 * world * self.shard_bytes
-        self.path = os.path.join("/dev/shm", name)
+        self.path = os.path.join(self.DIR, name)
         if rank == 0:
             with open(self.path, "wb") as f:
                 f.truncate(self.nbytes)

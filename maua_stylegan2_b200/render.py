@@ -454,7 +454,9 @@ def render(generator, latents, noise, offset, duration, batch_size, out_size, ou
         shared += [m for _, m in (rewrites or {}).values()]
         parallel.broadcast_inputs([t for t in shared if torch.is_tensor(t)], device=device)
         gather = parallel.AllGatherFrames(world)
-        ring = parallel.HostFrameRing(parallel.ring_name(), rank, world, batch_size, (h, w, 3))
+        if parallel.all_ranks_agree(parallel.HostFrameRing.fits(world, batch_size, (h, w, 3)), device):
+            ring = parallel.HostFrameRing(parallel.ring_name(), rank, world, batch_size, (h, w, 3))
+        # (no room in /dev/shm: rank 0 copies the gathered frames itself — one PCIe link instead of `world`)
     pipe = FramePipeline(generator, latents, noise, batch_size, truncation, bends, rewrites, randomize_noise,
                          fit_size=out_size, rank=rank, world=world)
     pipe.warmup()

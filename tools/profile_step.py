@@ -13,7 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--warmup", type=int, default=1)
 ap.add_argument("--batch", type=int, default=8)
-ap.add_argument("--precision", default="bf16x3")
+ap.add_argument("--precision", default=bench.DEFAULT_PRECISION)
 ap.add_argument("--ufd", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
