@@ -254,13 +254,14 @@ class FramePipeline:
             return self.starts[min(step * world + rank, nb - 1)]
 
         def finish(p):
-            p["done"].synchronize()
             if ring is not None:
-                ring.publish(p["step"])
+                # (the GPU published ready[rank] itself, behind the frame copy: nothing to wait for on the writer side)
                 if consume is not None:
                     consume(ring.frames_of(p["step"]).numpy()[:p["valid"]])
                     ring.release(p["step"])
-            elif consume is not None:
+                return
+            p["done"].synchronize()
+            if consume is not None:
                 consume(p["host"].numpy()[:p["valid"]])
 
         pending = None
@@ -299,6 +300,7 @@ class FramePipeline:
                     d2h.wait_event(ready)
                     dst.copy_(frames, non_blocking=True)
                     frames.record_stream(d2h)
+                    ring.publish_on_stream(i, self.device)     # ready[rank] = i + 1, written by the GPU after the frames
                     done = torch.cuda.Event()
                     done.record(d2h)
                 self.d2h_bytes += frames.numel()
@@ -328,6 +330,8 @@ class FramePipeline:
             elif graph_ok and full and work is not None:
                 self._slot_busy[i & 1] = (None, work)
         if pending is not None:
+            if ring is not None:
+                pending["done"].synchronize()   # this rank's last shard is in the ring before run() returns
             finish(pending)
         for slot in (0, 1):   # the last collectives are part of the job: the compute stream joins them before run() returns
             busy = self._slot_busy[slot]
