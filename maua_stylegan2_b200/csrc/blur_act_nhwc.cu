@@ -210,8 +210,7 @@ __global__ void __launch_bounds__(128 * (16 / RPT), 2) blur_act_nhwc_tma_kernel(
   const int p = tid >> 3;
   const int lx = p & 15;
   const int ly0 = (p >> 4) * RPT;
-  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(ep.out_hi);
-  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(ep.out_lo);
+  const bool hi = ep.out_hi != nullptr;
   const float nw = (ep.activate && ep.noise) ? __ldg(ep.noise_weight) : 0.f;
 
   int it = 0;
@@ -293,43 +292,65 @@ __global__ void __launch_bounds__(128 * (16 / RPT), 2) blur_act_nhwc_tma_kernel(
     }
 
     if (ox >= ow) continue;
+    // Epilogue.  ncu (1024^2 layer): this kernel is issue-bound, not memory-bound — 968 warp instructions per tile and warp,
+    // of which only 152 FFMA2 + 44 LDS are the FIR; the rest was scalar activation math (136 FMUL, 64 FADD, 32 FSETP/FSEL
+    // pairs) and 64-bit address arithmetic per row.  Now: packed f32x2 math with the activation gain folded into s_next,
+    // leaky-ReLU as max(v, slope*v) (min for slope > 1), and per-tile base pointers advanced by a constant row stride.
+    const bool act = ep.activate != 0;
+    const float slope = act ? ep.slope : 1.f, gain = act ? ep.act_scale : 1.f;
+    const bool use_max = slope <= 1.f;
+    const float2 sl2 = make_float2(slope, slope);
+    const float2 d_lo = make_float2(dm.x, dm.y), d_hi = make_float2(dm.z, dm.w);
+    const float2 b_lo = make_float2(bias.x, bias.y), b_hi = make_float2(bias.z, bias.w);
+    const float2 s_lo = make_float2(sn.x * gain, sn.y * gain), s_hi = make_float2(sn.z * gain, sn.w * gain);
+    const int oy_first = oy0 + ly0;
+    const long long pix0 = ((long long)b * oh + oy_first) * ow + ox;
+    const long long row_elems = (long long)ow * ch;
+    uint16_t* ph = hi ? reinterpret_cast<uint16_t*>(ep.out_hi) + pix0 * ch + cbase : nullptr;
+    uint16_t* pl = (hi && ep.out_fmt == 0) ? reinterpret_cast<uint16_t*>(ep.out_lo) + pix0 * ch + cbase : nullptr;
+    float* pn = ep.out_f32_nchw ? ep.out_f32_nchw + (((long long)b * ch + cbase) * oh + oy_first) * ow + ox : nullptr;
+    const long long plane = (long long)oh * ow;
+    const bool f16out = ep.out_fmt == 1;
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
-      const int oy = oy0 + ly0 + j;
-      if (oy >= oh) break;
-      // demodulation d[b,c] (when the transposed conv left it to this kernel): it commutes with the per-channel FIR
-      float v0 = __fmul_rn(acc[j].x, dm.x), v1 = __fmul_rn(acc[j].y, dm.y), v2 = __fmul_rn(acc[j].z, dm.z),
-            v3 = __fmul_rn(acc[j].w, dm.w);
-      if (ep.activate) {
-        const float nz = __fmul_rn(nw, nzv[j]);
-        v0 = lrelu_scaled(__fadd_rn(__fadd_rn(v0, nz), bias.x), ep.slope, ep.act_scale);
-        v1 = lrelu_scaled(__fadd_rn(__fadd_rn(v1, nz), bias.y), ep.slope, ep.act_scale);
-        v2 = lrelu_scaled(__fadd_rn(__fadd_rn(v2, nz), bias.z), ep.slope, ep.act_scale);
-        v3 = lrelu_scaled(__fadd_rn(__fadd_rn(v3, nz), bias.w), ep.slope, ep.act_scale);
+      if (oy_first + j >= oh) break;
+      const float nz = __fmul_rn(nw, nzv[j]);
+      const float2 nz2 = make_float2(nz, nz);
+      // v = FIR * d + (noise + bias)   [d: demodulation left to this kernel by the transposed conv, commutes with the FIR]
+      float2 v_lo = ffma2(make_float2(acc[j].x, acc[j].y), d_lo, fadd2(b_lo, nz2));
+      float2 v_hi = ffma2(make_float2(acc[j].z, acc[j].w), d_hi, fadd2(b_hi, nz2));
+      const float2 t_lo = fmul2(v_lo, sl2), t_hi = fmul2(v_hi, sl2);
+      if (use_max) {
+        v_lo = make_float2(fmaxf(v_lo.x, t_lo.x), fmaxf(v_lo.y, t_lo.y));
+        v_hi = make_float2(fmaxf(v_hi.x, t_hi.x), fmaxf(v_hi.y, t_hi.y));
+      } else {
+        v_lo = make_float2(fminf(v_lo.x, t_lo.x), fminf(v_lo.y, t_lo.y));
+        v_hi = make_float2(fminf(v_hi.x, t_hi.x), fminf(v_hi.y, t_hi.y));
       }
-      if (ep.out_f32_nchw) {
-        float* o = ep.out_f32_nchw + (((long long)b * ch + cbase) * oh + oy) * ow + ox;
-        const long long plane = (long long)oh * ow;
-        o[0] = v0; o[plane] = v1; o[2 * plane] = v2; o[3 * plane] = v3;
+      if (pn) {
+        float* o = pn + (long long)j * ow;
+        o[0] = v_lo.x * gain; o[plane] = v_lo.y * gain; o[2 * plane] = v_hi.x * gain; o[3 * plane] = v_hi.y * gain;
       }
-      if (hi && ep.out_fmt == 1) {   // "f16" activation format: one fp16 plane (8-byte stores)
-        const long long o = (((long long)b * oh + oy) * ow + ox) * ch + cbase;
-        uint2 ph;
-        ph.x = pack_f16x2_sat(v0 * sn.x, v1 * sn.y);
-        ph.y = pack_f16x2_sat(v2 * sn.z, v3 * sn.w);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.out_hi) + o) = ph;
-      } else if (hi) {
-        v0 *= sn.x; v1 *= sn.y; v2 *= sn.z; v3 *= sn.w;
-        const __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
-        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-        const __nv_bfloat162 l01 = __floats2bfloat162_rn(v0 - f01.x, v1 - f01.y);
-        const __nv_bfloat162 l23 = __floats2bfloat162_rn(v2 - f23.x, v3 - f23.y);
-        const long long o = (((long long)b * oh + oy) * ow + ox) * ch + cbase;
-        uint2 ph, pl;
-        ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
-        pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
-        *reinterpret_cast<uint2*>(hi + o) = ph;
-        *reinterpret_cast<uint2*>(lo + o) = pl;
+      if (ph) {
+        const float2 a_lo = fmul2(v_lo, s_lo), a_hi = fmul2(v_hi, s_hi);     // * gain * s_next
+        uint16_t* dst = ph + (long long)j * row_elems;
+        if (f16out) {   // "f16" activation format: one fp16 plane (8-byte stores)
+          uint2 o;
+          o.x = pack_f16x2_sat(a_lo.x, a_lo.y);
+          o.y = pack_f16x2_sat(a_hi.x, a_hi.y);
+          *reinterpret_cast<uint2*>(dst) = o;
+        } else {
+          const __nv_bfloat162 h01 = __floats2bfloat162_rn(a_lo.x, a_lo.y), h23 = __floats2bfloat162_rn(a_hi.x, a_hi.y);
+          const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+          const float2 neg1 = make_float2(-1.f, -1.f);
+          const float2 r01 = ffma2(f01, neg1, a_lo), r23 = ffma2(f23, neg1, a_hi);   // exact: a - hi
+          const __nv_bfloat162 l01 = __floats2bfloat162_rn(r01.x, r01.y), l23 = __floats2bfloat162_rn(r23.x, r23.y);
+          uint2 oh2, ol2;
+          oh2.x = *reinterpret_cast<const uint32_t*>(&h01); oh2.y = *reinterpret_cast<const uint32_t*>(&h23);
+          ol2.x = *reinterpret_cast<const uint32_t*>(&l01); ol2.y = *reinterpret_cast<const uint32_t*>(&l23);
+          *reinterpret_cast<uint2*>(dst) = oh2;
+          *reinterpret_cast<uint2*>(pl + (long long)j * row_elems) = ol2;
+        }
       }
     }
   }

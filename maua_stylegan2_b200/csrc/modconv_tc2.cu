@@ -358,15 +358,18 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       // (with fused ToRGB a warp owns whole tiles — first_job and first_job + EPI_GROUPS — and only needs their values)
       const int first_job_rgb = (egroup + EPI_GROUPS - job0) % EPI_GROUPS;
       float nzv[4] = {0.f, 0.f, 0.f, 0.f};
-      if (!UP && act && ep.noise) {
-        const float* nrow = ep.noise + (long long)b * ep.noise_bstride + gx;
+      if (!UP && act && ep.noise && gx < GW) {
+        // one 64-bit address per item, the R tiles are TH rows apart (a 32-bit constant step)
+        const float* np = ep.noise + (long long)b * ep.noise_bstride + (long long)(y0 + ty) * OW + gx;
+        const int rstep = TH * OW;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const int gy = y0 + r * TH + ty;
           const bool mine = !fuse_rgb || r == first_job_rgb || r == first_job_rgb + EPI_GROUPS;
-          if (mine && r < R && gy < GH && gx < GW) nzv[r] = __ldg(nrow + (long long)gy * OW);
+          if (mine && r < R && y0 + r * TH + ty < GH) nzv[r] = __ldg(np + r * rstep);
         }
       }
+      const long long pix_item = UP ? ((long long)b * OH + 2 * (y0 + ty)) * OW + 2 * gx
+                                    : ((long long)b * OH + (y0 + ty)) * OW + gx;
       mbar_wait(acc_full + 8 * as, pacc);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * acc_cols;
@@ -390,7 +393,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const int gph = !UP ? 0 : (p.n_groups == 2 ? (grp == 0 ? 3 * ph : 1 + ph) : grp * n_phase + ph);
         const int oy = UP ? 2 * gy + (gph >> 1) : gy, ox = UP ? 2 * gx + (gph & 1) : gx;
         const bool valid = in_grid && oy < OH && ox < OW;
-        const long long pix = valid ? (((long long)b * OH + oy) * OW + ox) : 0;
+        // output pixel index = per-item base (one 64-bit product per item) + a 32-bit offset per job
+        const long long pix = valid ? pix_item + (UP ? (2 * r * TH + (gph >> 1)) * OW + (gph & 1) : r * TH * OW) : 0;
         const float nz = UP ? 0.f : nwv * (r == 0 ? nzv[0] : (r == 1 ? nzv[1] : (r == 2 ? nzv[2] : nzv[3])));
         const uint32_t acc_col = (uint32_t)tile * blk_cols;
         float2 rgb0 = make_float2(0.f, 0.f), rgb1 = rgb0, rgb2 = rgb0;

@@ -29,6 +29,36 @@ __device__ __forceinline__ float skip_up2(const float* __restrict__ sp, int sh, 
   return v;
 }
 
+// skip_up2 for 4 consecutive output pixels ox0 .. ox0+3 (ox0 % 4 == 0) of one row: the 2 skip rows x 4 skip columns
+// they touch are loaded once (8 loads instead of 16, no per-pixel index arithmetic); out-of-range taps contribute an
+// exact fma(0, k, v) = v, and the FMA order per pixel (row-major over the 2x2 live taps) is skip_up2's, so the results
+// are bit-identical.
+__device__ __forceinline__ void skip_up2_x4(const float* __restrict__ sp, int sh, int sw, const float* kf, int oy, int ox0,
+                                            float out[4]) {
+  const int k0y = oy & 1, sy0 = (oy >> 1) - 1 + k0y, sx0 = (ox0 >> 1) - 1;
+  float sv[2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int iy = sy0 + a;
+    const bool row_ok = iy >= 0 && iy < sh;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int ix = sx0 + c;
+      sv[a][c] = (row_ok && ix >= 0 && ix < sw) ? __ldg(sp + (long long)iy * sw + ix) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k0x = j & 1, cj = (j + 1) >> 1;   // in0x - sx0 = {0,1,1,2}
+    float v = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) v = __fmaf_rn(sv[a][cj + e], kf[(3 - (k0y + 2 * a)) * 4 + (3 - (k0x + 2 * e))], v);
+    out[j] = v;
+  }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x, const float* __restrict__ wrgb,
                                                     const float* __restrict__ s, const float* __restrict__ bias,
@@ -178,10 +208,12 @@ __global__ void __launch_bounds__(256) rgb_finish_kernel(const float* __restrict
       o[0] = partial[i];
     }
     const float* sp = skip ? skip + plane * (h >> 1) * (w >> 1) : nullptr;
+    float sk[4] = {0.f, 0.f, 0.f, 0.f};
+    if (skip && VEC == 4) skip_up2_x4(sp, h >> 1, w >> 1, kf, oy, ox0, sk);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       o[j] = __fadd_rn(o[j], bb);
-      if (skip) o[j] = __fadd_rn(o[j], skip_up2(sp, h >> 1, w >> 1, kf, oy, ox0 + j));
+      if (skip) o[j] = __fadd_rn(o[j], VEC == 4 ? sk[j] : skip_up2(sp, h >> 1, w >> 1, kf, oy, ox0 + j));
     }
     if (VEC == 4) reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
     else y[i] = o[0];
@@ -211,10 +243,12 @@ __global__ void __launch_bounds__(256) rgb_finish_u8_kernel(const float* __restr
       float o[4] = {t.x, t.y, t.z, t.w};
       const float bb = bias ? __ldg(bias + k) : 0.f;
       const float* sp = skip ? skip + (b * 3 + k) * (h >> 1) * (w >> 1) : nullptr;
+      float sk[4] = {0.f, 0.f, 0.f, 0.f};
+      if (skip) skip_up2_x4(sp, h >> 1, w >> 1, kf, oy, ox0, sk);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float v = __fadd_rn(o[j], bb);
-        if (skip) v = __fadd_rn(v, skip_up2(sp, h >> 1, w >> 1, kf, oy, ox0 + j));
+        if (skip) v = __fadd_rn(v, sk[j]);
         v = fminf(fmaxf(v, -1.f), 1.f);
         v = __fmul_rn(__fadd_rn(v, 1.f), 127.5f);
         px[j * 3 + k] = (uint8_t)(int)v;
