@@ -61,7 +61,7 @@ class SynthHandle:
             L.call("maua_synth_prepare", self.h, self.plan.data_ptr(), self.plan.numel(), L.stream_ptr(self.device))
         self.batch = 0
         self.workspace = None
-        self.out_hw = None
+        self._workspaces = {}   # batch size -> workspace tensor (at most two, most recently bound last)
 
     def __del__(self):
         try:
@@ -72,15 +72,23 @@ class SynthHandle:
             pass
 
     def bind(self, batch):
+        """Lay the workspace out for `batch`.  The two most recent batch sizes keep their workspaces (a frame loop alternates
+        between full batches — possibly baked into captured CUDA graphs — and one short tail batch): re-binding a cached
+        size re-uses the SAME device addresses, so graphs captured for it stay valid."""
         if batch == self.batch:
             return
         if torch.cuda.is_current_stream_capturing():
             raise L.MauaError("maua_synth_bind inside CUDA-graph capture: run one eager forward at this batch size first")
         with torch.cuda.device(self.device):
-            self.workspace = None
-            nbytes = L.lib().maua_synth_workspace_bytes(self.h, batch)
-            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            L.call("maua_synth_bind", self.h, self.workspace.data_ptr(), nbytes, batch, L.stream_ptr(self.device))
+            ws = self._workspaces.pop(batch, None)
+            if ws is None:
+                while len(self._workspaces) >= 2:
+                    self._workspaces.pop(next(iter(self._workspaces)))   # drop the least recently bound size
+                nbytes = L.lib().maua_synth_workspace_bytes(self.h, batch)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._workspaces[batch] = ws                                  # most recent last
+            self.workspace = ws
+            L.call("maua_synth_bind", self.h, ws.data_ptr(), ws.numel(), batch, L.stream_ptr(self.device))
         self.batch = batch
 
     def forward(self, latent, noise, mean, psi_t, psi_s, out_hw, want_u8, want_rgb=True):

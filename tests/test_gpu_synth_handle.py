@@ -80,3 +80,18 @@ def test_handle_follows_weight_changes_and_graph_capture():
     torch.cuda.synchronize()
     want, _ = _forward(g, False, lat2, noise, psi, return_u8=True)
     assert torch.equal(out, want)
+    # the frame loop's short tail: an eager forward at ANOTHER batch size re-binds the handle; the captured graph's
+    # workspace must stay alive and valid (the handle keeps the two most recent batch sizes)
+    ws2 = g._synth_handle.workspace.data_ptr()
+    lat3, noise3, psi3 = _inputs(g, 3, 11)
+    tail_h, _ = _forward(g, True, lat3, noise3, psi3, return_u8=True)
+    tail_o, _ = _forward(g, False, lat3, noise3, psi3, return_u8=True)
+    assert torch.equal(tail_h, tail_o) and g._synth_handle.batch == 3
+    lat4, _, _ = _inputs(g, 2, 12)
+    static_lat.copy_(lat4)
+    graph.replay()
+    torch.cuda.synchronize()
+    want4, _ = _forward(g, False, lat4, noise, psi, return_u8=True)
+    assert torch.equal(out, want4)
+    _forward(g, True, lat4, noise, psi)            # eager again at batch 2: the cached workspace (same addresses) is re-bound
+    assert g._synth_handle.batch == 2 and g._synth_handle.workspace.data_ptr() == ws2
