@@ -275,6 +275,9 @@ def main():
         if rank != 0:
             return
         r = cpu_port_run(args.steps, args.warmup)
+        config = dict(config, reference_sample="each step = ONE frame of the batch-8 workload (a bounded sample: the CPU path "
+                                               "needs ~0.6-2 s per frame); kind 'port' = oracle restatement of the reference's CPU "
+                                               "path (oracle/stylegan2_oracle.py), thread count probed for the fastest setting")
         line = {"impl": "reference", "metric": "1024x1024 frames/sec", "value": r["fps"], "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": r["steps_done"], "warmup": args.warmup,
                 "ms_per_step": 1000.0 * r["seconds"] / max(r["steps_done"], 1), "higher_is_better": True,
@@ -453,7 +456,7 @@ def main():
             torch.cuda.synchronize()
             by = 4.0 * (x.numel() + y.numel())
             gbs = by / (s.elapsed_time(e) / reps * 1e-3) / 1e9
-            roof_ufd = {"kernel": "maua_upfirdn2d_f32 (blur_tile)", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
+            roof_ufd = {"kernel": "maua_upfirdn2d_f32 (blur_tile_pipe_kernel)", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
                         "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": ncu_traffic("maua_upfirdn2d_f32") if bb == 4 else None,
                         "algorithmic_bytes": by,
                         "shape": f"[{bb},32,2049,2049]->[{bb},32,2048,2048] fp32 (in+out {by / 1e9:.2f} GB > L2)"}
