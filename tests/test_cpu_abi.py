@@ -93,3 +93,35 @@ def test_state_dict_keys_match_reference_layout():
     extra = keys - set(sd.keys())
     assert all(k.endswith(".kernel") for k in extra), extra
     assert g.n_latent == 8 and g.num_layers == 7
+
+
+def test_cpu_tensor_branch_randomised_vs_index_spec():
+    """The CPU-tensor branch of op.upfirdn2d_raw on random native-ABI configurations (asymmetric rates, minor > 1, negative
+    pads) against the oracle's index-level restatement of the reference kernel (fp32 summation order differs: 1e-5)."""
+    import numpy as np
+    import torch
+
+    from maua_stylegan2_b200 import op
+    from oracle import ops_oracle as OO
+
+    rng = np.random.default_rng(2026)
+    checked = 0
+    for case in range(30):
+        major, minor = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        in_h, in_w = int(rng.integers(1, 16)), int(rng.integers(1, 16))
+        kh, kw = int(rng.integers(1, 7)), int(rng.integers(1, 6))
+        up_x, up_y, down_x, down_y = (int(v) for v in rng.integers(1, 4, 4))
+        px0, px1, py0, py1 = (int(v) for v in rng.integers(-2, 5, 4))
+        x = rng.standard_normal((major, in_h, in_w, minor)).astype(np.float32)
+        k = rng.standard_normal((kh, kw)).astype(np.float32)
+        out_h = (in_h * up_y + py0 + py1 - kh + down_y) // down_y
+        out_w = (in_w * up_x + px0 + px1 - kw + down_x) // down_x
+        if out_h <= 0 or out_w <= 0 or in_h * up_y + py0 + py1 < kh or in_w * up_x + px0 + px1 < kw:
+            continue
+        got = op.upfirdn2d_raw(torch.from_numpy(x), torch.from_numpy(k), up_x, up_y, down_x, down_y, px0, px1, py0, py1).numpy()
+        assert got.shape == (major, out_h, out_w, minor), case
+        for m in range(minor):
+            spec = OO.upfirdn2d_index(x[..., m], k, up_x, up_y, down_x, down_y, px0, px1, py0, py1, fma=False)
+            np.testing.assert_allclose(got[..., m], spec, rtol=0, atol=1e-5 * max(1.0, np.abs(spec).max()), err_msg=str(case))
+        checked += 1
+    assert checked >= 15

@@ -138,3 +138,46 @@ def test_upfirdn2d_full_size_properties():
     assert torch.equal(y2, y * 2.0)                            # scaling by a power of two commutes bit-exactly
     a = op.upfirdn2d(x[:, :4], k, pad=(1, 1))
     assert torch.equal(a, y[:, :4])                            # planes are independent
+
+
+def test_upfirdn2d_randomised_configurations_bit_exact_vs_index_spec():
+    """40 seeded random configurations of the native ABI form — major / minor > 1, asymmetric up / down per axis, kernels up
+    to 7x6, positive, zero and negative pads (crops), degenerate 1-pixel inputs — against the FMA-ordered index spec of
+    the reference kernel (op/upfirdn2d_kernel.cu:130-141,175-203).  Bit-exact; empty outputs must come back empty."""
+    from maua_stylegan2_b200 import op
+
+    rng = np.random.default_rng(2026)
+    n_checked = 0
+    for case in range(40):
+        major, minor = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        in_h, in_w = int(rng.integers(1, 20)), int(rng.integers(1, 20))
+        kh, kw = int(rng.integers(1, 8)), int(rng.integers(1, 7))
+        up_x, up_y = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        down_x, down_y = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        px0, px1, py0, py1 = (int(v) for v in rng.integers(-3, 6, 4))
+        x = rng.standard_normal((major, in_h, in_w, minor)).astype(np.float32)
+        k = rng.standard_normal((kh, kw)).astype(np.float32)
+        out_h = (in_h * up_y + py0 + py1 - kh + down_y) // down_y
+        out_w = (in_w * up_x + px0 + px1 - kw + down_x) // down_x
+        got = op.upfirdn2d_raw(torch.from_numpy(x).cuda(), torch.from_numpy(k).cuda(), up_x, up_y, down_x, down_y, px0, px1,
+                               py0, py1).cpu().numpy()
+        assert got.shape == (major, max(out_h, 0), max(out_w, 0), minor), (case, got.shape)
+        if out_h <= 0 or out_w <= 0:
+            continue
+        for m in range(minor):
+            spec = OO.upfirdn2d_index(x[..., m], k, up_x, up_y, down_x, down_y, px0, px1, py0, py1, fma=True)
+            assert np.array_equal(got[..., m], spec), f"case {case}: not bit-exact (max diff {np.abs(got[..., m] - spec).max()})"
+        n_checked += 1
+    assert n_checked >= 25
+
+
+def test_fused_bias_act_empty_and_large_inputs():
+    from maua_stylegan2_b200 import op
+
+    empty = torch.empty(0, 4, device="cuda")
+    assert op.fused_leaky_relu(empty, torch.zeros(4, device="cuda")).shape == (0, 4)
+    x = torch.randn(3, 5, 1 << 16, device="cuda")               # step_b = 65536, > 2^16 elements per bias entry
+    b = torch.randn(5, device="cuda")
+    y = op.fused_leaky_relu(x, b)
+    want = torch.nn.functional.leaky_relu(x + b[None, :, None], 0.2) * np.float32(2 ** 0.5)
+    assert torch.equal(y, want)
