@@ -6,8 +6,9 @@
     torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, NCCL)
 
 A step = one pass of the hot path over one batch of `--batch` frames (per GPU; weak scaling): style prologue, 17
-modulated convs (tcgen05 path, 3-product split-bf16 = parity grade), blur/noise/bias/lrelu epilogues, 9 ToRGB, uint8
-NHWC pack, and for N > 1 one NCCL all-gather of the uint8 frames.
+modulated convs (tcgen05 path; precision per `dtype`), blur/noise/bias/lrelu epilogues, 9 ToRGB, uint8 NHWC pack.  For
+N > 1 the frames are sharded rank-strided with no data-path collective (frames are independent); e2e brings
+them to rank 0's sink through a shared pinned host ring, every rank over its own PCIe link.
   value    : frames/s with latents/noise resident in HBM, CUDA events around exactly K steps, max over ranks.
   e2e      : frames/s through the public frame loop (maua_stylegan2_b200.render.FramePipeline): pinned host
              latents/noise -> H2D every step, synthesis, uint8 frames -> D2H into pinned memory, inside the timed region.
@@ -307,7 +308,6 @@ def main():
     latents_d = latents_h.to(device)
     noise_d = [n.to(device) if n is not None else None for n in noise_h]
     nb = n_frames // B
-    gather = AllGatherFrames(world) if world > 1 else None
 
     def step_local(i):
         # rank-strided batches; inputs are already resident in HBM
@@ -322,18 +322,22 @@ def main():
 
     def pipeline_run(lat, nz, n_steps, offset, to_host):
         """K steps of the public frame loop (render.FramePipeline: CUDA-graph replay of the captured forward, rank-strided
-        batches, one all-gather per step on NCCL's stream — the compute stream never waits for it).  Graph capture and
+        batches; `value` keeps each rank's frames in its own HBM, `e2e` moves them to rank 0's sink through the shared
+        pinned host ring — no data-path collective).  Graph capture and
         first-touch setup happen in warmup(), outside the timed region.  Returns (device ms, wall s, pipe)."""
         lo = offset * B * world
         idx = torch.tensor([j % n_frames for j in range(lo, lo + n_steps * B * world)]).to(lat.device)
         pipe = FramePipeline(g, lat[idx], [x[idx] if x is not None else None for x in nz], B, truncation=1.0, rank=rank,
                              world=world)
-        ring = None
+        ring = gather = None
         if to_host and world > 1 and all_ranks_agree(HostFrameRing.fits(world, B, (SIZE, SIZE, 3)), device):
             # every rank copies ITS frames device->host into a shared pinned ring over its own PCIe link; rank 0's sink
-            # reads world*B consecutive frames per step from host memory (render.render does the same)
+            # reads world*B consecutive frames per step from host memory (render.render does the same): frames are
+            # independent, so there is no data-path collective
             ring = HostFrameRing(f"{ring_name()}_{offset}_{n_steps}", rank, world, B, (SIZE, SIZE, 3))
-        elif to_host and rank == 0:   # (also the N > 1 fallback when /dev/shm has no room: rank 0 copies the gathered frames)
+        elif to_host and world > 1:   # /dev/shm has no room: one NCCL all-gather per step, rank 0 copies the gathered frames
+            gather = AllGatherFrames(world)
+        if to_host and ring is None and rank == 0:
             pipe.prepare_host_buffers((SIZE, SIZE, 3))
         pipe.warmup()
         sink_bytes = [0]

@@ -9,7 +9,8 @@ get_bends(args) / get_rewrites(args) / get_truncation(args) — discovered by na
 
 What differs: audio features, latents and noise are produced and kept ON DEVICE (no `.cpu()` / pin / re-upload per batch),
 the generator is the B200 `Generator`, the frame loop is `render.FramePipeline`, and with `torchrun` frames are sharded
-over the GPUs of the box (one all-gather of uint8 frames per step) instead of `th.nn.DataParallel`.
+over the GPUs of the box (each rank delivers its own uint8 frames through a shared pinned host ring) instead of
+`th.nn.DataParallel`.
 Extra keyword arguments: `audio=(array, sr)` bypasses `load_audio` (synthetic audio), `sink=` replaces ffmpeg.
 """
 import argparse

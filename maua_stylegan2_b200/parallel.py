@@ -1,10 +1,10 @@
-"""Multi-GPU frame sharding: one process per GPU (torchrun), rank-strided batches, ONE NCCL all-gather of the finished
-uint8 NHWC frames per step over NVLink.  The reference's only multi-GPU render mode is
-single-process `th.nn.DataParallel` (generate_audiovisual.py:54-55), which re-broadcasts the 121 MB of weights every
-step and gathers fp32 images to GPU 0; here weights are replicated once and 3 B/pixel cross the switch.
-
-The frame path has no other exchange step, so there is no other collective (frames are independent given their
-latents / noise / truncation rows)."""
+"""Multi-GPU frame sharding: one process per GPU (torchrun), rank-strided batches.  Frames are
+independent given their latents / noise / truncation rows, so the data path has NO collective: every rank copies its own
+uint8 NHWC frames device->host into a shared pinned ring (HostFrameRing) that rank 0's sink reads in frame order.  The
+inputs are broadcast once before the loop (broadcast_inputs).  AllGatherFrames — ONE NCCL all-gather of the finished
+frames per step over NVLink, 3 B/pixel — is the fallback when /dev/shm cannot hold the ring, and the option for
+on-device consumers.  The reference's only multi-GPU render mode is single-process `th.nn.DataParallel`
+(generate_audiovisual.py:54-55), which re-broadcasts the 121 MB of weights every step and gathers fp32 images to GPU 0."""
 import datetime
 import os
 

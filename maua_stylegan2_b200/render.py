@@ -240,11 +240,11 @@ class FramePipeline:
               with all frames on the device; without `ring`, rank 0 copies all of them to the host.
           ring (parallel.HostFrameRing): every rank copies ITS shard device->host into a shared pinned ring over its own
               PCIe link and rank 0's sink reads the consecutive frames from host memory (no single-link ceiling).
-        Both may be given (the collective then serves on-device consumers only).  Short tails are padded by repeating the
+        Both may be given (the collective then serves on-device consumers only); with neither, at world > 1 every rank
+        keeps its own frames (rank 0's `consume` then sees only rank 0's batches).  Short tails are padded by repeating the
         last frame and trimmed before `consume`.  H2D of step i+1 (copy stream) and D2H of step i-1 (d2h stream) overlap
         the synthesis of step i (compute stream); the compute stream never waits for a collective."""
-        sharded = gather is not None or ring is not None
-        world, rank = (self.world, self.rank) if sharded else (1, 0)
+        world, rank = self.world, self.rank   # (world > 1 without gather/ring: the frames stay sharded in each rank's HBM)
         nb = len(self.starts)
         steps = (nb + world - 1) // world
         cur = torch.cuda.current_stream(self.device)
@@ -283,6 +283,8 @@ class FramePipeline:
             if frames.shape[0] < self.batch:  # short tail: pad by repeating the last frame (equal-size collective)
                 frames = torch.cat([frames, frames[-1:].expand(self.batch - frames.shape[0], -1, -1, -1)], 0)
             valid = min(self.n_frames - i * world * self.batch, world * self.batch)
+            if gather is None and ring is None:
+                valid = min(self.n_frames - n, self.batch)      # unexchanged: this rank's own batch only
             work = None
             if gather is not None:
                 work, out = gather(frames, i & 1)   # async collective on NCCL's stream; compute does not wait for it
@@ -435,9 +437,10 @@ def render(generator, latents, noise, offset, duration, batch_size, out_size, ou
            truncation=1.0, bends=[], rewrites={}, randomize_noise=False, ffmpeg_preset="slow", sink=None):
     """Drop-in for the reference's `render.render` (render.py:14-192).  Under torchrun (torch.distributed initialised,
     see parallel.init_from_env — what `generate(dataparallel=True)` does) the frames are sharded over the ranks of the
-    box: inputs are made identical on every rank (broadcast from rank 0), rank r renders batches i*world + r, one NCCL
-    all-gather of the uint8 frames per step runs beside a sharded device->host copy into a shared pinned ring, and only
-    rank 0 owns the sink / ffmpeg process.  Returns the FramePipeline (its h2d/d2h byte counters are per rank)."""
+    box: inputs are made identical on every rank (broadcast from rank 0), rank r renders batches i*world + r, every rank
+    copies its own uint8 frames device->host into a shared pinned ring (no data-path collective; when /dev/shm has no room,
+    or MAUA_FRAME_EXCHANGE=gather: one NCCL all-gather per step and rank 0 copies), and only rank 0 owns the sink / ffmpeg
+    process.  Returns the FramePipeline (its h2d/d2h byte counters are per rank)."""
     from . import parallel
 
     sizes = {512: (512, 512), 1024: (1024, 1024), 1920: (1920, 1080), 1080: (1080, 1920)}
@@ -457,10 +460,14 @@ def render(generator, latents, noise, offset, duration, batch_size, out_size, ou
         shared = [latents] + noise + [truncation] + [b.get("modulation") for b in bends]
         shared += [m for _, m in (rewrites or {}).values()]
         parallel.broadcast_inputs([t for t in shared if torch.is_tensor(t)], device=device)
-        gather = parallel.AllGatherFrames(world)
-        if parallel.all_ranks_agree(parallel.HostFrameRing.fits(world, batch_size, (h, w, 3)), device):
+        want_ring = os.environ.get("MAUA_FRAME_EXCHANGE", "ring") != "gather"
+        if want_ring and parallel.all_ranks_agree(parallel.HostFrameRing.fits(world, batch_size, (h, w, 3)), device):
+            # frames are independent and the only consumer is rank 0's sink, which reads host memory: no collective at all
             ring = parallel.HostFrameRing(parallel.ring_name(), rank, world, batch_size, (h, w, 3))
-        # (no room in /dev/shm: rank 0 copies the gathered frames itself — one PCIe link instead of `world`)
+        else:
+            # no room in /dev/shm (or MAUA_FRAME_EXCHANGE=gather): one NCCL all-gather per step and rank 0 copies the
+            # gathered frames itself — one PCIe link instead of `world`
+            gather = parallel.AllGatherFrames(world)
     pipe = FramePipeline(generator, latents, noise, batch_size, truncation, bends, rewrites, randomize_noise,
                          fit_size=out_size, rank=rank, world=world)
     pipe.warmup()
