@@ -143,7 +143,8 @@ __device__ __forceinline__ void tma_load_tile_4d(uint32_t dst, const CUtensorMap
 template <int RPT>
 __global__ void __launch_bounds__(128 * (16 / RPT), 2) blur_act_nhwc_tma_kernel(const __grid_constant__ CUtensorMap tm_u,
                                                                    const float* __restrict__ k4, MauaConvEpilogue ep,
-                                                                   int batch, int ch, int hu, int wu, int n_tiles) {
+                                                                   int batch, int ch, int hu, int wu, int n_tiles,
+                                                                   FastDiv fd_ncg, FastDiv fd_tx, FastDiv fd_ty) {
   using namespace ptx;
   constexpr uint32_t TILE_BYTES = BIN * BIN * BCH * 4;
   extern __shared__ uint8_t smem_raw[];
@@ -168,13 +169,14 @@ __global__ void __launch_bounds__(128 * (16 / RPT), 2) blur_act_nhwc_tma_kernel(
   }
   __syncthreads();
 
+  // (multiply-shift divisions: the three runtime divisions were ~75 of the ~480 instructions per thread and tile)
   auto decode = [&](int t, int& cg, int& ox0, int& oy0, int& b) {
-    cg = t % ncg;
-    int r = t / ncg;
-    ox0 = (r % tiles_x) * BT;
-    r /= tiles_x;
-    oy0 = (r % tiles_y) * BT;
-    b = r / tiles_y;
+    const int r0 = fast_div(t, fd_ncg);
+    cg = t - r0 * ncg;
+    const int r1 = fast_div(r0, fd_tx);
+    ox0 = (r0 - r1 * tiles_x) * BT;
+    b = fast_div(r1, fd_ty);
+    oy0 = (r1 - b * tiles_y) * BT;
   };
   auto issue = [&](int t, int stage) {
     int cg, ox0, oy0, b;
@@ -385,10 +387,14 @@ extern "C" int maua_blur_act_nhwc(const float* u, const float* k4, const MauaCon
     MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(blur_act_nhwc_tma_kernel<4>), smem));
     const int n_sm = device_sm_count();
     const int grid = (int)(n_tiles < n_sm * 2 ? n_tiles : n_sm * 2);
+    const FastDiv f0 = make_fastdiv((uint32_t)(ch / BCH)), f1 = make_fastdiv((uint32_t)ceil_div(ow, BT)),
+                  f2 = make_fastdiv((uint32_t)ceil_div(oh, BT));
     if (rpt == 8)
-      blur_act_nhwc_tma_kernel<8><<<grid, 256, smem, as_stream(stream)>>>(tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles);
+      blur_act_nhwc_tma_kernel<8><<<grid, 256, smem, as_stream(stream)>>>(tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles,
+                                                                           f0, f1, f2);
     else
-      blur_act_nhwc_tma_kernel<4><<<grid, 512, smem, as_stream(stream)>>>(tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles);
+      blur_act_nhwc_tma_kernel<4><<<grid, 512, smem, as_stream(stream)>>>(tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles,
+                                                                           f0, f1, f2);
     MAUA_CHECK_LAUNCH("blur_act_nhwc(tma)");
     return MAUA_OK;
   }

@@ -131,6 +131,21 @@ __device__ __forceinline__ void st_global_v8_b32(void* p, uint32_t a0, uint32_t 
                : "memory");
 }
 
+// Exact x / d for 0 <= x < 2^31 and a runtime-constant d >= 1 without the ~25-instruction integer-division sequence:
+// q = (umulhi(x, m) + x) >> s with m = floor(2^32 * (2^s - d) / d) + 1, s = ceil(log2 d)  (round-up method, 33-bit magic).
+struct FastDiv { uint32_t m, s; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t sh = 0;
+  while ((1ull << sh) < d) ++sh;
+  f.s = sh;
+  f.m = (uint32_t)((((1ull << sh) - d) << 32) / d + 1);
+  return f;
+}
+__device__ __forceinline__ int fast_div(int x, FastDiv f) {
+  return (int)((__umulhi((uint32_t)x, f.m) + (uint32_t)x) >> f.s);
+}
+
 __device__ __forceinline__ float lrelu_scaled(float v, float slope, float scale) {
   return __fmul_rn(v > 0.f ? v : __fmul_rn(v, slope), scale);
 }

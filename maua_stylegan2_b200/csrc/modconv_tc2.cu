@@ -34,6 +34,9 @@ constexpr int TH = 16, TW = 8;  // one M tile = 16 rows x 8 columns
 #define MAUA_EPI_GROUPS 3
 #endif
 constexpr int EPI_GROUPS = MAUA_EPI_GROUPS;
+#ifndef MAUA_TC_PAIR_DEFAULT
+#define MAUA_TC_PAIR_DEFAULT 0   // CTA pairs: 0 = off unless MAUA_TC_PAIR asks, 1 = on for BN >= 128 split-bf16 layers
+#endif
 #ifndef MAUA_ROLE_WARPS
 #define MAUA_ROLE_WARPS (MAUA_EPI_GROUPS >= 4 ? 4 : 2)
 #endif
@@ -63,6 +66,10 @@ struct Params {
   // role warp decodes every item: 160 of the ~1000 epilogue instructions per item were these, ncu source view)
   uint32_t fd_m[4], fd_s[4];   // 0: per_group, 1: n_tiles, 2: tiles_x, 3: tiles_y   q = (umulhi(x, m) + x) >> s, x < 2^31
   int per_group;
+  // CTA pairs (template PAIR): a work item is one (n tile, phase group) for TWO pixel tiles — cluster rank r takes pixel
+  // tile 2*pp + r of pixel-pair pp (n_ptiles odd: the last pair's rank 1 works on an all-out-of-range tile)
+  int pair;
+  int n_ptiles;          // pixel tiles = tiles_x * tiles_y * B
   int dbg;               // MAUA_TC_DBG (timing experiments, results invalid): 1 = empty epilogue, 2 = no A loads after the
                          // first, 4 = epilogue stops after the TMEM loads, 8 = epilogue without TMEM loads
 };
@@ -95,7 +102,11 @@ __device__ __forceinline__ float lrelu_s(float v, float slope, float scale) { re
 //   N = BN MMAs into the same accumulator, 4 = a*[w_hi|w_lo] as ONE N = 2*BN MMA (BN <= 64: small-N MMAs are bound by the
 //   4 KB A-operand fetch, so halving the A planes AND the MMA count nearly halves the tensor-pipe time of those layers).
 // A template parameter (not p.cat / p.a_planes) so that the issue loop is branch-free.
-template <int KC, bool UP, int MODE>
+// PAIR: two CTAs of a cluster (one TPC) run every MMA together (cta_group::2, M = 256 = the two CTAs' pixel tiles, the
+//   weight tile split in halves between them).  The wide layers (N = 256 per MMA) are bound by shared-memory bandwidth
+//   with single-CTA MMAs — 4 KB of A + 8 KB of B per 128-cycle MMA plus the TMA refill of the B ring — and a pair
+//   halves the B bytes each SM reads and receives.  Only the leader (rank 0) issues MMAs; both load, both drain.
+template <int KC, bool UP, int MODE, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -106,7 +117,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_stage = (uint32_t)p.a_planes * p.a_plane;
-  const uint32_t b_half = (uint32_t)p.BN * ROW, b_stage = 2 * b_half;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int bn_cta = PAIR ? p.BN >> 1 : p.BN;    // weight rows this CTA holds per tap / K chunk
+  const uint32_t b_half = (uint32_t)bn_cta * ROW, b_stage = 2 * b_half;
   const uint32_t a_base = smem0;
   const uint32_t b_base = a_base + (uint32_t)p.SA * a_stage;
   const uint32_t bar_base = b_base + (uint32_t)p.SB * b_stage;
@@ -127,15 +140,20 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     if (p.b_planes > 1) prefetch_tmap(&tm_b_lo);
     for (int i = 0; i < p.SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    for (int i = 0; i < p.AS; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4 * EPI_GROUPS); }
+    // (pairs: the epilogue warps of BOTH CTAs release an accumulator stage on the leader's barrier)
+    for (int i = 0; i < p.AS; ++i) {
+      mbar_init(acc_full + 8 * i, 1);
+      mbar_init(acc_empty + 8 * i, (PAIR ? 2 : 1) * 4 * EPI_GROUPS);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_2cta(tmem_slot, p.tmem_cols); tmem_relinquish_2cta(); }
+    else { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers exist before any remote arrive / TMA completion targets them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -156,12 +174,24 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       rest = fdiv(item, 1);
       n_tile = item - rest * p.n_tiles;
     }
+    n0 = n_tile * p.BN;
+    if (PAIR) {
+      rest = 2 * rest + (int)rank;           // pixel-pair -> this CTA's pixel tile
+      if (rest >= p.n_ptiles) {              // odd tile count: nothing to do for the last pair's rank 1 — a tile below the
+        x0 = 0;                              // image (TMA zero-fills the halo, every epilogue store is bounds-checked)
+        y0 = p.tiles_y * TH * p.R;
+        b = p.B - 1;
+        return;
+      }
+    }
     const int q1 = fdiv(rest, 2);            // rest / tiles_x
     x0 = (rest - q1 * p.tiles_x) * TW;
     b = fdiv(q1, 3);                         // q1 / tiles_y
     y0 = (q1 - b * p.tiles_y) * TH * p.R;
-    n0 = n_tile * p.BN;
   };
+  // persistent walk: CTA (or CTA pair) i takes items i, i + step, ...
+  const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int istep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   auto tap_list = [&](int grp) -> const TapList& {
     return c_taps[!UP ? 0 : (p.n_groups == 1 ? 1 : (p.n_groups == 2 ? 2 + grp : 4 + grp))];
   };
@@ -177,42 +207,66 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     // ================================ TMA producer ================================
     int ia = 0, ib = 0;
     uint32_t pa = 0, pb = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    // pairs: every load of either CTA is counted on the LEADER's full barrier (it alone waits for operands); the leader's
+    // expect_tx covers both CTAs' boxes, the empty barriers stay per CTA (signalled by the multicast commit)
+    const uint32_t a_full_tx = PAIR ? mapa_u32(a_full, 0) : a_full, b_full_tx = PAIR ? mapa_u32(b_full, 0) : b_full;
+    const uint32_t ncta = PAIR ? 2u : 1u;
+    const int brow = PAIR ? (int)rank * bn_cta : 0;   // this CTA's half of the weight tile
+    for (int item = item0; item < p.n_items; item += istep) {
       int n0, grp, x0, y0, b;
       decode(item, n0, grp, x0, y0, b);
       const TapList& tl = tap_list(grp);
       for (int kc = 0; kc < p.n_kchunks; ++kc) {
         const int c0 = kc * KC;
         mbar_wait(a_empty + 8 * ia, pa ^ 1);
-        if ((p.dbg & 2) && item != (int)blockIdx.x) {
+        if (!PAIR && (p.dbg & 2) && item != item0) {
           mbar_arrive(a_full + 8 * ia);
         } else {
-        mbar_expect_tx(a_full + 8 * ia, halo_bytes * (uint32_t)p.a_planes);
+        if (rank == 0) mbar_expect_tx(a_full + 8 * ia, ncta * halo_bytes * (uint32_t)p.a_planes);
         const uint32_t dst = a_base + ia * a_stage;
-        tma_load_4d(dst, &tm_a_hi, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
-        if (p.a_planes > 1) tma_load_4d(dst + p.a_plane, &tm_a_lo, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
+        if (PAIR) {
+          tma_load_4d_2cta(dst, &tm_a_hi, a_full_tx + 8 * ia, c0, x0 - 1, y0 - 1, b);
+          if (p.a_planes > 1) tma_load_4d_2cta(dst + p.a_plane, &tm_a_lo, a_full_tx + 8 * ia, c0, x0 - 1, y0 - 1, b);
+        } else {
+          tma_load_4d(dst, &tm_a_hi, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
+          if (p.a_planes > 1) tma_load_4d(dst + p.a_plane, &tm_a_lo, a_full + 8 * ia, c0, x0 - 1, y0 - 1, b);
+        }
         }
         if (++ia == p.SA) { ia = 0; pa ^= 1; }
 #pragma unroll 1
         for (int t = 0; t < tl.n; ++t) {
-          if (p.resident_b && item != (int)blockIdx.x) break;  // weights already resident in shared memory
+          if (p.resident_b && item != item0) break;  // weights already resident in shared memory
           mbar_wait(b_empty + 8 * ib, pb ^ 1);
-          mbar_expect_tx(b_full + 8 * ib, p.b_planes > 1 ? b_stage : b_half);
+          if (rank == 0) mbar_expect_tx(b_full + 8 * ib, ncta * (p.b_planes > 1 ? b_stage : b_half));
           const uint32_t dstb = b_base + ib * b_stage;
-          tma_load_3d(dstb, &tm_b_hi, b_full + 8 * ib, c0, n0, tl.t[t].tap);
-          if (p.b_planes > 1) tma_load_3d(dstb + b_half, &tm_b_lo, b_full + 8 * ib, c0, n0, tl.t[t].tap);
+          if (PAIR) {
+            tma_load_3d_2cta(dstb, &tm_b_hi, b_full_tx + 8 * ib, c0, n0 + brow, tl.t[t].tap);
+            if (p.b_planes > 1) tma_load_3d_2cta(dstb + b_half, &tm_b_lo, b_full_tx + 8 * ib, c0, n0 + brow, tl.t[t].tap);
+          } else {
+            tma_load_3d(dstb, &tm_b_hi, b_full + 8 * ib, c0, n0, tl.t[t].tap);
+            if (p.b_planes > 1) tma_load_3d(dstb + b_half, &tm_b_lo, b_full + 8 * ib, c0, n0, tl.t[t].tap);
+          }
           if (++ib == p.SB) { ib = 0; pb ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && (!PAIR || rank == 0)) {
     // ================================ MMA issuer ================================
     // the whole warp walks the loop (uniform control flow); one elected lane issues the tcgen05 instructions
     const bool leader = elect_one_sync();
     // The issue loop must stay far below the ~50 cycles a 128x32x16 MMA occupies the tensor pipe: all descriptor
     // fields are folded into per-stage base values up front; per MMA only 64-bit adds of small constants remain.
-    const uint32_t idesc = MODE >= 3 ? make_idesc_f16(128, (uint32_t)p.BN) : make_idesc_bf16(128, (uint32_t)p.BN);
-    const uint32_t idesc2 = MODE >= 3 ? make_idesc_f16(128, (uint32_t)(2 * p.BN)) : make_idesc_bf16(128, (uint32_t)(2 * p.BN));
+    constexpr uint32_t MM = PAIR ? 256u : 128u;
+    const uint32_t idesc = MODE >= 3 ? make_idesc_f16(MM, (uint32_t)p.BN) : make_idesc_bf16(MM, (uint32_t)p.BN);
+    const uint32_t idesc2 = MODE >= 3 ? make_idesc_f16(MM, (uint32_t)(2 * p.BN)) : make_idesc_bf16(MM, (uint32_t)(2 * p.BN));
+    auto mma = [](uint32_t acc, uint64_t da, uint64_t db, uint32_t id, uint32_t accumulate) {
+      if (PAIR) umma_bf16_2cta(acc, da, db, id, accumulate);
+      else umma_bf16(acc, da, db, id, accumulate);
+    };
+    auto commit = [](uint32_t bar) {
+      if (PAIR) umma_commit_2cta(bar);
+      else umma_commit(bar);
+    };
     const uint64_t sbo_field = (uint64_t)((((uint32_t)p.HW_ * ROW) >> 4) & 0x3FFF) << 32;
     const uint64_t da0 = (make_kmajor_desc(a_base, ROW) & ~(0x3FFFull << 32)) | sbo_field;  // A stage 0, hi plane
     const uint64_t db0 = make_kmajor_desc(b_base, ROW);                                      // B stage 0, hi plane
@@ -222,7 +276,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     constexpr int mode = MODE;
     int ia = 0, ib = 0, as = 0;
     uint32_t pa = 0, pb = 0, pacc = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    for (int item = item0; item < p.n_items; item += istep) {
       int n0, grp, x0, y0, b;
       decode(item, n0, grp, x0, y0, b);
       const TapList& tl = tap_list(grp);
@@ -241,7 +295,7 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll 1
           for (int t = 0; t < tl.n; ++t) {
             const Tap tp = tl.t[t];
-            if (!p.resident_b || item == (int)blockIdx.x) {
+            if (!p.resident_b || item == item0) {
               mbar_wait(b_full + 8 * ib, pb);
               tc_fence_after();
             }
@@ -255,42 +309,42 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 const uint64_t dah = dah0 + (uint64_t)r * rstep16, dal = dah + a_plane16;
                 const uint32_t acc = acc0 + (uint32_t)r * blk_cols;
                 if (mode == 2) {  // [hi*hi | hi*lo] in one N = 2*BN MMA (B stage = hi rows then lo rows), then lo*hi
-                  umma_bf16(acc, dah, dbh, idesc2, first);
-                  umma_bf16(acc, dah + 2, dbh + 2, idesc2, 1u);
-                  umma_bf16(acc, dal, dbh, idesc, 1u);
-                  umma_bf16(acc, dal + 2, dbh + 2, idesc, 1u);
+                  mma(acc, dah, dbh, idesc2, first);
+                  mma(acc, dah + 2, dbh + 2, idesc2, 1u);
+                  mma(acc, dal, dbh, idesc, 1u);
+                  mma(acc, dal + 2, dbh + 2, idesc, 1u);
                 } else if (mode == 4) {  // fp16: a * [w_hi | w_lo], one N = 2*BN MMA per K-step
-                  umma_bf16(acc, dah, dbh, idesc2, first);
-                  umma_bf16(acc, dah + 2, dbh + 2, idesc2, 1u);
+                  mma(acc, dah, dbh, idesc2, first);
+                  mma(acc, dah + 2, dbh + 2, idesc2, 1u);
                 } else if (mode == 3) {  // fp16: a * w_hi + a * w_lo into the same accumulator
-                  umma_bf16(acc, dah, dbh, idesc, first);
-                  umma_bf16(acc, dah + 2, dbh + 2, idesc, 1u);
-                  umma_bf16(acc, dah, dbl, idesc, 1u);
-                  umma_bf16(acc, dah + 2, dbl + 2, idesc, 1u);
+                  mma(acc, dah, dbh, idesc, first);
+                  mma(acc, dah + 2, dbh + 2, idesc, 1u);
+                  mma(acc, dah, dbl, idesc, 1u);
+                  mma(acc, dah + 2, dbl + 2, idesc, 1u);
                 } else {
-                  umma_bf16(acc, dah, dbh, idesc, first);
-                  umma_bf16(acc, dah + 2, dbh + 2, idesc, 1u);
+                  mma(acc, dah, dbh, idesc, first);
+                  mma(acc, dah + 2, dbh + 2, idesc, 1u);
                   if (mode == 1) {
-                    umma_bf16(acc, dah, dbl, idesc, 1u);
-                    umma_bf16(acc, dah + 2, dbl + 2, idesc, 1u);
-                    umma_bf16(acc, dal, dbh, idesc, 1u);
-                    umma_bf16(acc, dal + 2, dbh + 2, idesc, 1u);
+                    mma(acc, dah, dbl, idesc, 1u);
+                    mma(acc, dah + 2, dbl + 2, idesc, 1u);
+                    mma(acc, dal, dbh, idesc, 1u);
+                    mma(acc, dal + 2, dbh + 2, idesc, 1u);
                   }
                 }
               }
             }
             started |= 1u << tp.phase;
-            if (!p.resident_b && leader) umma_commit(b_empty + 8 * ib);
+            if (!p.resident_b && leader) commit(b_empty + 8 * ib);
             if (++ib == p.SB) { ib = 0; pb ^= 1; }
           }
-          if (leader) umma_commit(a_empty + 8 * ia);
+          if (leader) commit(a_empty + 8 * ia);
           if (++ia == p.SA) { ia = 0; pa ^= 1; }
         }
       };
       if (p.R == 4) run_item(std::integral_constant<int, 4>{});
       else if (p.R == 2) run_item(std::integral_constant<int, 2>{});
       else run_item(std::integral_constant<int, 1>{});
-      if (leader) umma_commit(acc_full + 8 * as);
+      if (leader) commit(acc_full + 8 * as);
       if (++as == p.AS) { as = 0; pacc ^= 1; }
     }
   } else if (warp >= ROLE_WARPS) {
@@ -331,7 +385,8 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     float* const sm_w = vec + 3 * Cout;
     int cur_b = -1;
     int job0 = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, job0 = (job0 + R) % EPI_GROUPS) {
+    const uint32_t acc_empty_tx = PAIR ? mapa_u32(acc_empty, 0) : acc_empty;   // the leader's barrier
+    for (int item = item0; item < p.n_items; item += istep, job0 = (job0 + R) % EPI_GROUPS) {
       int n0, grp, x0, y0, b;
       decode(item, n0, grp, x0, y0, b);
       if (!UP && b != cur_b) {  // uniform over the epilogue warps: they all walk the same item sequence
@@ -552,16 +607,21 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       // accumulator stage drained: hand it back to the MMA issuer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(acc_empty_tx + 8 * as);
+        else mbar_arrive(acc_empty + 8 * as);
+      }
       if (++as == p.AS) { as = 0; pacc ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the other may still signal / read it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (PAIR) tmem_dealloc_2cta(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -704,7 +764,17 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   p.n_groups = best_groups;
   p.n_phase = nphase / best_groups;
   int cols = 32;
-  const uint32_t a_stage = a_planes * p.a_plane, b_stage = 2u * bn * kc * 2u;
+  // CTA pairs (cta_group::2) for the split-bf16 layers with wide N tiles: those are bound by shared-memory bandwidth
+  // (see the kernel's PAIR note).  MAUA_TC_PAIR=0 disables, =1 enables wherever the mode allows (read per call).
+  const char* pair_env = getenv("MAUA_TC_PAIR");
+  const int pair_req = pair_env ? atoi(pair_env) : MAUA_TC_PAIR_DEFAULT;
+  const long long ptiles = tiles_x * p.tiles_y * batch;
+  const bool pair = pair_req != 0 && n_products == 3 && !p.cat && bn >= (pair_req == 1 ? 128 : 32) && ptiles >= 2 &&
+                    ptiles < (1LL << 30);
+  p.pair = pair ? 1 : 0;
+  p.n_ptiles = (int)(ptiles < (1LL << 30) ? ptiles : 0);
+  const int bn_cta = pair ? bn / 2 : bn;
+  const uint32_t a_stage = a_planes * p.a_plane, b_stage = 2u * bn_cta * kc * 2u;
   p.SA = (2 * a_stage + 4 * b_stage <= budget) ? 2 : 1;
   int sb = (int)((budget - (uint32_t)p.SA * a_stage) / b_stage);
   // small layers: keep ALL weight tiles of the layer in shared memory for the lifetime of the persistent CTA
@@ -716,7 +786,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   const size_t smem = (size_t)p.SA * a_stage + (size_t)p.SB * b_stage + 8 * (2 * p.SA + 2 * p.SB + 6) + 1024 +
                       6 * (size_t)cout * 4 + 32;
   if (smem > 227 * 1024) return unsupported;
-  const long long items = tiles_x * p.tiles_y * batch * p.n_tiles * p.n_groups;
+  const long long items = (pair ? (ptiles + 1) / 2 : ptiles) * p.n_tiles * p.n_groups;
   if (items >= (1LL << 31)) return MAUA_E_UNSUPPORTED;
   p.n_items = (int)items;
   p.per_group = (int)(items / p.n_groups);
@@ -736,14 +806,14 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   while (cols < p.AS * blk_cols * R * p.n_phase) cols <<= 1;
   p.tmem_cols = (uint32_t)cols;
   const int n_sm = device_sm_count();
-  const long long grid = items < n_sm ? items : n_sm;
+  const long long grid = pair ? 2 * (items < n_sm / 2 ? items : n_sm / 2) : (items < n_sm ? items : n_sm);
   static const bool debug = [] { const char* e = getenv("MAUA_TC_DEBUG"); return e && e[0] == '1'; }();
   if (debug)
     fprintf(stderr, "[modconv_tc2] %s B%d %d->%d @%dx%d: R=%d BN=%d cat=%d groups=%d resB=%d AS=%d SA=%d SB=%d smem=%zuKB tmem=%u items=%lld grid=%lld\n",
             up ? "up" : "same", batch, cin, cout, h, w, R, bn, p.cat, p.n_groups, p.resident_b, p.AS, p.SA, p.SB, smem / 1024, p.tmem_cols, items, grid);
 
-  set_conv_config("v2 up=%d R=%d BN=%d cat=%d groups=%d prod=%d resB=%d AS=%d SA=%d SB=%d items=%lld grid=%lld", up, R, bn, p.cat,
-                  p.n_groups, n_products, p.resident_b, p.AS, p.SA, p.SB, items, grid);
+  set_conv_config("v2 up=%d R=%d BN=%d cat=%d groups=%d prod=%d resB=%d AS=%d SA=%d SB=%d items=%lld grid=%lld pair=%d", up, R, bn,
+                  p.cat, p.n_groups, n_products, p.resident_b, p.AS, p.SA, p.SB, items, grid, p.pair);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   const auto swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const cuuint64_t adims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
@@ -751,7 +821,7 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   const cuuint32_t abox[4] = {(cuuint32_t)kc, (cuuint32_t)p.HW_, (cuuint32_t)p.HH_, 1};
   const cuuint64_t bdims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
   const cuuint64_t bstr[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
-  const cuuint32_t bbox[3] = {(cuuint32_t)kc, (cuuint32_t)bn, 1};
+  const cuuint32_t bbox[3] = {(cuuint32_t)kc, (cuuint32_t)bn_cta, 1};   // (pairs: each CTA loads half of the N tile's rows)
   int rc;
   const auto dt = n_products == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   if ((rc = tmap::encode(&ta_hi, dt, x_hi, 4, adims, astr, abox, swz))) return rc;
@@ -768,20 +838,37 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   }
 #define MAUA_TC2_LAUNCH(KCV, UPV, MODEV)                                                                            \
   do {                                                                                                              \
-    MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(modconv_tc2_kernel<KCV, UPV, MODEV>), smem));    \
-    modconv_tc2_kernel<KCV, UPV, MODEV><<<(unsigned)grid, THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep);      \
+    MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(modconv_tc2_kernel<KCV, UPV, MODEV, false>), smem)); \
+    modconv_tc2_kernel<KCV, UPV, MODEV, false><<<(unsigned)grid, THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep); \
   } while (0)
   const int mode = n_products == 1 ? 0 : (n_products == 2 ? (p.cat ? 4 : 3) : (p.cat ? 2 : 1));
+#define MAUA_TC2_LAUNCH_PAIR(KCV, UPV, MODEV)                                                                       \
+  do {                                                                                                              \
+    auto kern = modconv_tc2_kernel<KCV, UPV, MODEV, true>;                                                          \
+    MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem));                                    \
+    cudaLaunchConfig_t cfg = {};                                                                                    \
+    cfg.gridDim = dim3((unsigned)grid);                                                                             \
+    cfg.blockDim = dim3(THREADS);                                                                                   \
+    cfg.dynamicSmemBytes = smem;                                                                                    \
+    cfg.stream = st;                                                                                                \
+    cudaLaunchAttribute attr[1];                                                                                    \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                               \
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;                       \
+    cfg.attrs = attr;                                                                                               \
+    cfg.numAttrs = 1;                                                                                               \
+    MAUA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, p, ep));                             \
+  } while (0)
 #define MAUA_TC2_MODES(UPV)                                                   \
   switch (mode) {                                                             \
     case 0: MAUA_TC2_LAUNCH(32, UPV, 0); break;                               \
-    case 1: MAUA_TC2_LAUNCH(32, UPV, 1); break;                               \
+    case 1: if (pair) MAUA_TC2_LAUNCH_PAIR(32, UPV, 1); else MAUA_TC2_LAUNCH(32, UPV, 1); break; \
     case 2: MAUA_TC2_LAUNCH(32, UPV, 2); break;                               \
     case 3: MAUA_TC2_LAUNCH(32, UPV, 3); break;                               \
     default: MAUA_TC2_LAUNCH(32, UPV, 4); break;                              \
   }
   if (up) { MAUA_TC2_MODES(true) } else { MAUA_TC2_MODES(false) }
 #undef MAUA_TC2_MODES
+#undef MAUA_TC2_LAUNCH_PAIR
 #undef MAUA_TC2_LAUNCH
   MAUA_CHECK_LAUNCH("modconv_tc(v2)");
   return MAUA_OK;

@@ -147,12 +147,25 @@ __global__ void __launch_bounds__(256) torgb_small_kernel(const float* __restric
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
   if (p < hw) {
     const float* xb = x + (long long)b * cin * hw + p;
-    // same accumulation order per partial (ascending c), partials combined in ascending group order below
-    for (int c = cg; c < cin; c += 8) {
-      const float xv = __ldg(xb + (long long)c * hw);
-      a0 = fmaf(xv, wr[c], a0);
-      a1 = fmaf(xv, wr[cin + c], a1);
-      a2 = fmaf(xv, wr[2 * cin + c], a2);
+    // same accumulation order per partial (ascending c), partials combined in ascending group order below.
+    // Eight activation loads are issued before the first dependent FMA: with one load per iteration the 64-step chain
+    // paid the L2 latency 64 times (ncu: 17 us for the 8x8 layer, whose data is 1 MB).
+    for (int c0 = cg; c0 < cin; c0 += 64) {
+      float xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + 8 * u;
+        xv[u] = c < cin ? __ldg(xb + (long long)c * hw) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + 8 * u;
+        if (c < cin) {
+          a0 = fmaf(xv[u], wr[c], a0);
+          a1 = fmaf(xv[u], wr[cin + c], a1);
+          a2 = fmaf(xv[u], wr[2 * cin + c], a2);
+        }
+      }
     }
   }
   part[0][cg][lane] = a0;

@@ -55,6 +55,13 @@ struct MauaSynth {
   uint8_t* arena[2] = {nullptr, nullptr};
   size_t arena_bytes = 0;
   float* image[2] = {nullptr, nullptr};
+  // ToRGB branch: the skip-connection chain (ToRGB of layer i + upsampled image of layer i-2) only meets the conv chain
+  // again at the last layer, so it runs on a side stream (fork / join with events: capturable, the graph gets a parallel
+  // branch) and fills the tails of the persistent conv kernels instead of serialising ~9 latency-bound launches.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+  int side_device = -1;
+  bool overlap = true;
 };
 
 namespace maua {
@@ -130,7 +137,20 @@ int maua_synth_create(const MauaSynthDesc* desc, MauaSynth** out) {
   return MAUA_OK;
 }
 
-void maua_synth_destroy(MauaSynth* h) { delete h; }
+void maua_synth_destroy(MauaSynth* h) {
+  if (!h) return;
+  if (h->side) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(h->side_device);
+    cudaStreamSynchronize(h->side);
+    cudaEventDestroy(h->ev_main);
+    cudaEventDestroy(h->ev_side);
+    cudaStreamDestroy(h->side);
+    cudaSetDevice(cur);
+  }
+  delete h;
+}
 
 size_t maua_synth_plan_bytes(const MauaSynth* h) { return h ? h->plan_bytes + maua::ALIGN : 0; }
 
@@ -216,6 +236,17 @@ int maua_synth_bind(MauaSynth* h, void* workspace, size_t workspace_bytes, int b
   MAUA_CHECK_CUDA(cudaMemcpyAsync(h->jobs_dev, jobs.data(), sizeof(MauaStyleJob) * h->n_jobs, cudaMemcpyHostToDevice, st));
   MAUA_CHECK_CUDA(cudaMemsetAsync(h->splitk, 0, SPLITK_BYTES, st));
   MAUA_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (!h->side) {   // (created here, not in forward(): bind is the call that is documented as not capturable)
+    const char* e = getenv("MAUA_SYNTH_OVERLAP");
+    h->overlap = !(e && atoi(e) == 0);
+    int lo = 0, hi = 0;
+    MAUA_CHECK_CUDA(cudaGetDevice(&h->side_device));
+    MAUA_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    // highest priority: its few short blocks take the first SMs a draining conv kernel frees
+    MAUA_CHECK_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
+    MAUA_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+    MAUA_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
+  }
   h->ws = workspace;
   h->ws_bytes = workspace_bytes;
   h->batch = batch;
@@ -238,8 +269,19 @@ int maua_synth_forward(MauaSynth* h, const float* latent, int latent_rows, const
   float* image = nullptr;
   int image_slot = 0;
   const size_t n_layers = h->layers.size();
+  cudaStream_t main_st = as_stream(stream);
+  int side_reads_arena = -1;   // arena the newest ToRGB kernel on the side stream still reads (-1: side stream joined)
+  auto join_side = [&]() -> int {
+    if (side_reads_arena >= 0) {
+      MAUA_CHECK_CUDA(cudaStreamWaitEvent(main_st, h->ev_side, 0));
+      side_reads_arena = -1;
+    }
+    return MAUA_OK;
+  };
   for (size_t li = 0; li < n_layers; ++li) {
     const LayerState& ls = h->layers[li];
+    // this layer overwrites arena[li & 1]: a ToRGB kernel of layer li-2 that still reads its map there must be done
+    if (side_reads_arena == (int)(li & 1) && (rc = join_side()) != MAUA_OK) return rc;
     const LayerState* nxt = li + 1 < n_layers ? &h->layers[li + 1] : nullptr;
     const MauaSynthLayer& l = ls.l;
     uint8_t* a = h->arena[li & 1];
@@ -313,6 +355,17 @@ int maua_synth_forward(MauaSynth* h, const float* latent, int latent_rows, const
       const float* upk = image ? l.rgb_up_kernel : nullptr;
       MAUA_CHECK_ARG(!image || upk, "synth_forward: layer %d needs rgb_up_kernel for its skip connection", (int)li);
       const bool bytes_only = last_rgb && out_u8 && !out_rgb && ls.fuse_rgb && ls.out_w % 4 == 0;
+      // every ToRGB but the last goes to the side stream, behind this layer's conv; the last one joins the branches
+      const bool on_side = h->overlap && !last_rgb;
+      void* rgb_stream = stream;
+      if (on_side) {
+        MAUA_CHECK_CUDA(cudaEventRecord(h->ev_main, main_st));
+        MAUA_CHECK_CUDA(cudaStreamWaitEvent(h->side, h->ev_main, 0));
+        rgb_stream = h->side;
+      } else if ((rc = join_side()) != MAUA_OK) {
+        return rc;
+      }
+      stream = rgb_stream;
       if (bytes_only)   // last ToRGB straight to uint8 NHWC: the full-resolution fp32 image is never written
         rc = maua_rgb_finish_u8(partial, l.rgb_bias, image, upk, out_u8, batch, ls.out_h, ls.out_w, stream);
       else if (ls.fuse_rgb)
@@ -320,7 +373,12 @@ int maua_synth_forward(MauaSynth* h, const float* latent, int latent_rows, const
       else
         rc = maua_torgb_f32(y, l.rgb_weight, ls.rgb_s, l.rgb_bias, image, upk, dst, batch, l.cout, ls.out_h, ls.out_w,
                             (float)(1.0 / std::sqrt((double)l.cout)), stream);
+      stream = main_st;
       if (rc != MAUA_OK) return rc;
+      if (on_side) {
+        MAUA_CHECK_CUDA(cudaEventRecord(h->ev_side, h->side));
+        side_reads_arena = (int)(li & 1);
+      }
       image = dst;
       image_slot ^= 1;
       if (last_rgb && out_u8 && !bytes_only) {
@@ -329,6 +387,7 @@ int maua_synth_forward(MauaSynth* h, const float* latent, int latent_rows, const
       }
     }
   }
+  if ((rc = join_side()) != MAUA_OK) return rc;
   MAUA_CHECK_ARG(image != nullptr, "synth_forward: the network has no ToRGB layer");
   return MAUA_OK;
 }

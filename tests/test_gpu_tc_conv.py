@@ -214,6 +214,47 @@ def test_tc2_forced_configurations(case, forces, monkeypatch):
         _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 3, scale)
 
 
+# CTA pairs (cta_group::2, MAUA_TC_PAIR): M = 256 MMAs over two CTAs of a cluster, the weight tile split between them.
+# MAUA_TC_PAIR=2 pairs every split-bf16 non-concat configuration with BN >= 32; results must equal the unpaired kernel's
+# bit for bit (same MMAs, same accumulation order per output element) — and match the fp64 reference.
+PAIR_CASES = [
+    ((2, 128, 256, 64, 64, False), [None, "1,256,0,1", "1,128,0,1", "2,128,0,1", "2,64,0,1", "4,32,0,1"]),
+    ((1, 64, 128, 72, 40, False), [None, "2,128,0,1", "1,64,0,1"]),                  # ragged tiles, odd pixel-tile count
+    ((3, 64, 64, 48, 24, False), ["1,64,0,1", "2,32,0,1"]),                          # 27 pixel tiles at R=1: dummy peer tile
+    ((1, 128, 256, 33, 17, True), [None, "1,256,0,4", "1,256,0,2", "2,128,0,2", "1,128,0,1"]),
+    ((2, 64, 128, 64, 32, True), [None, "1,128,0,2", "2,64,0,2", "4,32,0,4"]),
+]
+
+
+@pytest.mark.parametrize("case,forces", PAIR_CASES)
+def test_tc2_cta_pairs_match_single_cta_kernel(case, forces, monkeypatch):
+    from maua_stylegan2_b200 import _lib as L
+
+    b, cin, cout, h, w, up = case
+    x, wt, s, d, noise, nw, bias, s_next, scale = _case_tensors(b, cin, cout, h, w, up, 501 + cout + h)
+    ref, raw = _reference(x, wt, s, d, noise, nw, bias, up, scale)
+    for f in forces:
+        if f is None:
+            monkeypatch.delenv("MAUA_TC_FORCE", raising=False)
+        else:
+            monkeypatch.setenv("MAUA_TC_FORCE", f)
+        monkeypatch.setenv("MAUA_TC_PAIR", "0")
+        y0, h0, l0, u0 = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 3, scale)
+        cfg0 = L.last_conv_config()
+        if not cfg0.startswith("v2 "):
+            continue   # (the default policy may route a small case to v1: nothing to pair)
+        assert cfg0.endswith("pair=0"), cfg0
+        monkeypatch.setenv("MAUA_TC_PAIR", "2")
+        y1, h1, l1, u1 = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 3, scale)
+        cfg1 = L.last_conv_config()
+        assert cfg1.endswith("pair=1"), (f, cfg1)
+        print(cfg1)
+        _check(ref, raw, y1, h1, l1, u1, s_next, up)
+        for a, c in ((y0, y1), (h0, h1), (l0, l1), (u0, u1)):
+            if a is not None:
+                assert torch.equal(a, c), f"pair kernel differs from the single-CTA kernel ({f})"
+
+
 # The "f16" activation format (precision="mixed": the >= 512^2 layers): one fp16 activation plane, fp16 (hi, lo) weights.
 # The only rounding is the 11-bit activation operand: per-layer error ~2e-4 of the tensor max (bar: 6e-4 here, 1e-3 on
 # the network); the fp16 OUTPUT plane adds the consumer's own operand rounding (2^-11 per element).
