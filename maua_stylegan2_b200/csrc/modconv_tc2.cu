@@ -18,6 +18,8 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include <cmath>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "tmap.cuh"
@@ -35,7 +37,7 @@ constexpr int TH = 16, TW = 8;  // one M tile = 16 rows x 8 columns
 #endif
 constexpr int EPI_GROUPS = MAUA_EPI_GROUPS;
 #ifndef MAUA_TC_PAIR_DEFAULT
-#define MAUA_TC_PAIR_DEFAULT 0   // CTA pairs: 0 = off unless MAUA_TC_PAIR asks, 1 = on for BN >= 128 split-bf16 layers
+#define MAUA_TC_PAIR_DEFAULT 1   // CTA pairs: 1 = on for the BN >= 128 split-bf16 layers (MAUA_TC_PAIR=0 turns them off, =2: BN >= 32)
 #endif
 #ifndef MAUA_ROLE_WARPS
 #define MAUA_ROLE_WARPS (MAUA_EPI_GROUPS >= 4 ? 4 : 2)
@@ -740,6 +742,17 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
       else if (up && pg < 4 && !force_groups) pg <<= 1;
       else if (pbn > 64 && !ep.rgb_out) pbn >>= 1;
       else break;
+    }
+    // Wave quantisation of the persistent grid: 512->512 @64^2 at batch 8 is 512 (R=1, BN=256) items = 3.46 waves of the
+    // 148 SMs (74 CTA pairs), i.e. a 4th wave at 46 % occupancy.  Half-width N tiles double the item count (6.9 -> 7
+    // waves); measured with CTA pairs: 0.280 ms vs 0.294 ms.  Only taken when it recovers >= 8 % of the grid.
+    if (!up && n_products == 3 && pbn == 256 && !ep.rgb_out && feasible(pr, 128, pcat, pg)) {
+      const double slots = device_sm_count();
+      auto wave_eff = [&](int bn) {
+        const double it = (double)n_ctas(pr, bn, pg);
+        return it / (std::ceil(it / slots) * slots);
+      };
+      if (wave_eff(256) < 0.9 && wave_eff(128) > wave_eff(256) + 0.08) pbn = 128;
     }
     if (feasible(pr, pbn, pcat, pg)) { best_r = pr; best_bn = pbn; best_cat = pcat; best_groups = pg; }
     else search();

@@ -40,7 +40,13 @@ def test_conv_kernels_are_tcgen05_tma_tmem_code():
             assert "CALL.ABS" not in body, f"{name}: an external call (printf?) breaks uniform-register MMA issue"
     v2 = {k: v for k, v in _functions(_sass("modconv_tc2.o")).items() if "modconv_tc2_kernel" in k}
     # {same-res, transposed} x {bf16: 1 product, 3 products, concat; fp16: two N=BN MMAs, one N=2*BN concat MMA}
-    assert len(v2) == 10
+    # + the CTA-pair (cta_group::2) form of the 3-product kernel
+    assert len(v2) == 12
+    pairs = {k: v for k, v in v2.items() if "UTCHMMA.2CTA" in v}
+    assert len(pairs) == 2, sorted(pairs)
+    for name, body in pairs.items():
+        for mnemonic in ("UTMALDG.4D.2CTA", "UTMALDG.3D.2CTA", "UTCBAR.2CTA.MULTICAST", "UTCATOMSWS.2CTA", "UCGABAR_ARV"):
+            assert mnemonic in body, (name, mnemonic)
     for name, body in v2.items():
         assert "FFMA2" in body or "FMUL2" in body, name   # packed fp32 epilogue
         # the unrolled R = 4 tap issues its MMAs back to back: at least one run of >= 8 UTCHMMA within 24 instructions

@@ -21,9 +21,11 @@ if os.path.exists(f"{G}/{tag}_ufd.json"):
     shutil.copy(f"{G}/{tag}_ufd.json", f"{P}/{rnd}_upfirdn2d.json")
 # per-layer source-level captures (tools/prof_layer.sh): top stall lines + the headline counters
 with open(f"{P}/{rnd}_ncu_layers.txt", "w") as f:
-    f.write("ncu --set full --import-source on --clock-control none, ONE launch of maua_modconv_tc per layer (batch 8, fp16 "
-            "activation format = precision 'mixed'), tools/prof_layer.sh; top stall lines of the SASS view + counters\n")
-    for name, what in (("l13", "128->64 @256 up"), ("l14", "64->64 @512 +rgb"), ("l15", "64->32 @512 up"), ("l16", "32->32 @1024 +rgb")):
+    f.write("ncu --set full --import-source on --clock-control none, ONE launch of maua_modconv_tc per layer (batch 8, "
+            "operand formats of precision 'mixed'; transposed layers in the product form: raw phases, no d), tools/prof_layer.sh; top stall lines of the SASS view + counters\n")
+    for name, what in (("l08", "512->512 @64 (split bf16, CTA pairs)"), ("l10", "256->256 @128 (split bf16, CTA pairs)"),
+                       ("l13", "128->64 @256 up (fp16 format)"), ("l14", "64->64 @512 +rgb (fp16 format)"),
+                       ("l15", "64->32 @512 up (fp16 format)"), ("l16", "32->32 @1024 +rgb (fp16 format)")):
         top, det = f"{G}/{tag}_{name}_top.txt", f"{G}/{tag}_{name}_details.txt"
         if not os.path.exists(top):
             continue

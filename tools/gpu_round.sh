@@ -22,9 +22,11 @@ timeout 400 ncu --set full --clock-control none -k regex:'hpss|gaussian_filter|n
     --launch-skip 100 -c 110 -o $O/${TAG}_audio python tools/bench_audio.py --seconds 30 --no-oracle > $O/${TAG}_audio.log 2>&1
 ncu -i $O/${TAG}_audio.ncu-rep --page raw --csv > $O/${TAG}_audio_raw.csv 2>/dev/null
 python tools/ncu_summary.py $O/${TAG}_audio_raw.csv > $O/${TAG}_audio_summary.txt 2>&1
-for L in "32,32,1024,0:l16" "64,32,512,1:l15" "64,64,512,0:l14" "128,64,256,1:l13"; do
-  bash tools/prof_layer.sh ${TAG}_${L#*:} "${L%:*}" - 2
-  python tools/ncu_source_top.py $O/${TAG}_${L#*:}_source.csv 14 > $O/${TAG}_${L#*:}_top.txt 2>&1
+# per-layer source-level captures: "cin,cout,h,up:name:products" (3 = split bf16, CTA pairs for BN >= 128; 2 = fp16 format)
+for L in "32,32,1024,0:l16:2" "64,32,512,1:l15:2" "64,64,512,0:l14:2" "128,64,256,1:l13:2" "256,256,128,0:l10:3" "512,512,64,0:l08:3"; do
+  SHAPE=${L%%:*}; REST=${L#*:}; NAME=${REST%%:*}; PROD=${REST#*:}
+  bash tools/prof_layer.sh ${TAG}_${NAME} "$SHAPE" - $PROD
+  python tools/ncu_source_top.py $O/${TAG}_${NAME}_source.csv 14 > $O/${TAG}_${NAME}_top.txt 2>&1
 done
 find $O -name '*.ncu-rep' -size +30M -delete
 tail -3 $O/${TAG}_pytest.log; cat $O/${TAG}_bench.json | head -c 1500; cat $O/${TAG}_ufd.json

@@ -22,6 +22,8 @@ ap.add_argument("--force", default=None)
 ap.add_argument("--prod", type=int, default=3, help="3 = split bf16, 2 = fp16 activation format, 1 = single bf16 product")
 ap.add_argument("--min-res", type=int, default=64, help="only layers whose output is at least this wide")
 ap.add_argument("--out-f16", type=int, default=-1, help="epilogue output format (default: fp16 plane iff --prod 2)")
+ap.add_argument("--up-d", action="store_true", help="transposed layers: demodulate in the conv epilogue (stand-alone form); "
+                                                    "default = the product form (raw phases, d applied by blur_act)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 chan = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * a.cm, 128: 128 * a.cm, 256: 64 * a.cm, 512: 32 * a.cm,
@@ -49,7 +51,8 @@ def run(cin, cout, h, up, fuse, last, force):
     out_f16 = (a.prod == 2) if a.out_f16 < 0 else bool(a.out_f16)
     d = torch.rand(B, cout, device=dev) + 0.5
     ep = L.ConvEpilogue()
-    ep.d = d.data_ptr()
+    if not up or a.up_d:
+        ep.d = d.data_ptr()
     keep = [d]
     if up:
         u = torch.empty(B, 2 * h + 1, 2 * h + 1, cout, device=dev)
