@@ -140,7 +140,11 @@ __device__ __forceinline__ void tma_load_tile_4d(uint32_t dst, const CUtensorMap
 }
 
 // RPT = output rows per thread (8: 256 threads, 4: 512 threads — more warps to hide LDS / epilogue latency)
-template <int RPT>
+// FMT = what the epilogue writes, fixed at compile time for the two forms the generator uses (ncu, 1024^2 layer: 749 warp
+//   instructions per tile and warp, ~90 of them the per-row format branches and the min/max pair of a runtime slope test):
+//   0 = bf16 (hi, lo) planes only, 1 = one fp16 plane only, 2 = anything (fp32 NCHW map, no operand planes, ...).
+// The leaky-ReLU is max(v, slope*v): the host routes slope > 1 to the generic kernel above.
+template <int RPT, int FMT>
 __global__ void __launch_bounds__(128 * (16 / RPT), 2) blur_act_nhwc_tma_kernel(const __grid_constant__ CUtensorMap tm_u,
                                                                    const float* __restrict__ k4, MauaConvEpilogue ep,
                                                                    int batch, int ch, int hu, int wu, int n_tiles,
@@ -300,7 +304,6 @@ __global__ void __launch_bounds__(128 * (16 / RPT), 2) blur_act_nhwc_tma_kernel(
     // leaky-ReLU as max(v, slope*v) (min for slope > 1), and per-tile base pointers advanced by a constant row stride.
     const bool act = ep.activate != 0;
     const float slope = act ? ep.slope : 1.f, gain = act ? ep.act_scale : 1.f;
-    const bool use_max = slope <= 1.f;
     const float2 sl2 = make_float2(slope, slope);
     const float2 d_lo = make_float2(dm.x, dm.y), d_hi = make_float2(dm.z, dm.w);
     const float2 b_lo = make_float2(bias.x, bias.y), b_hi = make_float2(bias.z, bias.w);
@@ -308,11 +311,12 @@ __global__ void __launch_bounds__(128 * (16 / RPT), 2) blur_act_nhwc_tma_kernel(
     const int oy_first = oy0 + ly0;
     const long long pix0 = ((long long)b * oh + oy_first) * ow + ox;
     const long long row_elems = (long long)ow * ch;
-    uint16_t* ph = hi ? reinterpret_cast<uint16_t*>(ep.out_hi) + pix0 * ch + cbase : nullptr;
-    uint16_t* pl = (hi && ep.out_fmt == 0) ? reinterpret_cast<uint16_t*>(ep.out_lo) + pix0 * ch + cbase : nullptr;
-    float* pn = ep.out_f32_nchw ? ep.out_f32_nchw + (((long long)b * ch + cbase) * oh + oy_first) * ow + ox : nullptr;
+    uint16_t* ph = (FMT != 2 || hi) ? reinterpret_cast<uint16_t*>(ep.out_hi) + pix0 * ch + cbase : nullptr;
+    uint16_t* pl = (FMT == 0 || (FMT == 2 && hi && ep.out_fmt == 0)) ? reinterpret_cast<uint16_t*>(ep.out_lo) + pix0 * ch + cbase
+                                                                      : nullptr;
+    float* pn = (FMT == 2 && ep.out_f32_nchw) ? ep.out_f32_nchw + (((long long)b * ch + cbase) * oh + oy_first) * ow + ox : nullptr;
     const long long plane = (long long)oh * ow;
-    const bool f16out = ep.out_fmt == 1;
+    const bool f16out = FMT == 1 || (FMT == 2 && ep.out_fmt == 1);
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
       if (oy_first + j >= oh) break;
@@ -322,18 +326,13 @@ __global__ void __launch_bounds__(128 * (16 / RPT), 2) blur_act_nhwc_tma_kernel(
       float2 v_lo = ffma2(make_float2(acc[j].x, acc[j].y), d_lo, fadd2(b_lo, nz2));
       float2 v_hi = ffma2(make_float2(acc[j].z, acc[j].w), d_hi, fadd2(b_hi, nz2));
       const float2 t_lo = fmul2(v_lo, sl2), t_hi = fmul2(v_hi, sl2);
-      if (use_max) {
-        v_lo = make_float2(fmaxf(v_lo.x, t_lo.x), fmaxf(v_lo.y, t_lo.y));
-        v_hi = make_float2(fmaxf(v_hi.x, t_hi.x), fmaxf(v_hi.y, t_hi.y));
-      } else {
-        v_lo = make_float2(fminf(v_lo.x, t_lo.x), fminf(v_lo.y, t_lo.y));
-        v_hi = make_float2(fminf(v_hi.x, t_hi.x), fminf(v_hi.y, t_hi.y));
-      }
-      if (pn) {
+      v_lo = make_float2(fmaxf(v_lo.x, t_lo.x), fmaxf(v_lo.y, t_lo.y));
+      v_hi = make_float2(fmaxf(v_hi.x, t_hi.x), fmaxf(v_hi.y, t_hi.y));
+      if (FMT == 2 && pn) {
         float* o = pn + (long long)j * ow;
         o[0] = v_lo.x * gain; o[plane] = v_lo.y * gain; o[2 * plane] = v_hi.x * gain; o[3 * plane] = v_hi.y * gain;
       }
-      if (ph) {
+      if (FMT != 2 || ph) {
         const float2 a_lo = fmul2(v_lo, s_lo), a_hi = fmul2(v_hi, s_hi);     // * gain * s_next
         uint16_t* dst = ph + (long long)j * row_elems;
         if (f16out) {   // "f16" activation format: one fp16 plane (8-byte stores)
@@ -372,7 +371,8 @@ extern "C" int maua_blur_act_nhwc(const float* u, const float* k4, const MauaCon
   if (batch == 0) return MAUA_OK;
   MAUA_CHECK_ARG(batch <= 65535, "blur_act_nhwc: batch too large");
   const int oh = hu - 1, ow = wu - 1;
-  if (ch % BCH == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0) {
+  const bool slope_ok = !ep_host->activate || ep_host->slope <= 1.f;   // lrelu as max(v, slope*v)
+  if (ch % BCH == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0 && slope_ok) {
     CUtensorMap tm;
     const cuuint64_t dims[4] = {(cuuint64_t)ch, (cuuint64_t)wu, (cuuint64_t)hu, (cuuint64_t)batch};
     const cuuint64_t strides[3] = {(cuuint64_t)ch * 4, (cuuint64_t)wu * ch * 4, (cuuint64_t)hu * wu * ch * 4};
@@ -383,18 +383,24 @@ extern "C" int maua_blur_act_nhwc(const float* u, const float* k4, const MauaCon
     MAUA_CHECK_ARG(n_tiles < (1LL << 31), "blur_act_nhwc: too many tiles");
     const size_t smem = 2 * (size_t)BIN * BIN * BCH * 4 + 16 + 128;
     static const int rpt = [] { const char* e = getenv("MAUA_BLUR_RPT"); return e ? atoi(e) : 8; }();
-    MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(blur_act_nhwc_tma_kernel<8>), smem));
-    MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(blur_act_nhwc_tma_kernel<4>), smem));
     const int n_sm = device_sm_count();
     const int grid = (int)(n_tiles < n_sm * 2 ? n_tiles : n_sm * 2);
     const FastDiv f0 = make_fastdiv((uint32_t)(ch / BCH)), f1 = make_fastdiv((uint32_t)ceil_div(ow, BT)),
                   f2 = make_fastdiv((uint32_t)ceil_div(oh, BT));
-    if (rpt == 8)
-      blur_act_nhwc_tma_kernel<8><<<grid, 256, smem, as_stream(stream)>>>(tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles,
-                                                                           f0, f1, f2);
-    else
-      blur_act_nhwc_tma_kernel<4><<<grid, 512, smem, as_stream(stream)>>>(tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles,
-                                                                           f0, f1, f2);
+    // operand planes only (what every transposed layer of the generator that feeds a tensor-core layer writes) -> the
+    // compile-time formats; anything else (fp32 NCHW map for ToRGB / bends, no planes) -> the generic epilogue
+    const int fmt = (ep_host->out_f32_nchw || !ep_host->out_hi || rpt != 8) ? 2 : (ep_host->out_fmt == 1 ? 1 : 0);
+#define MAUA_BLUR_LAUNCH(RPTV, FMTV)                                                                                  \
+  do {                                                                                                                \
+    MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(blur_act_nhwc_tma_kernel<RPTV, FMTV>), smem));      \
+    blur_act_nhwc_tma_kernel<RPTV, FMTV><<<grid, 128 * (16 / RPTV), smem, as_stream(stream)>>>(                       \
+        tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles, f0, f1, f2);                                               \
+  } while (0)
+    if (rpt != 8) MAUA_BLUR_LAUNCH(4, 2);
+    else if (fmt == 0) MAUA_BLUR_LAUNCH(8, 0);
+    else if (fmt == 1) MAUA_BLUR_LAUNCH(8, 1);
+    else MAUA_BLUR_LAUNCH(8, 2);
+#undef MAUA_BLUR_LAUNCH
     MAUA_CHECK_LAUNCH("blur_act_nhwc(tma)");
     return MAUA_OK;
   }
