@@ -164,13 +164,15 @@ __global__ void __launch_bounds__(128 * (16 / RPT), 2) blur_act_nhwc_tma_kernel(
   const int oh = hu - 1, ow = wu - 1;
   const int tiles_x = (ow + BT - 1) / BT, tiles_y = (oh + BT - 1) / BT, ncg = ch / BCH;
 
-  if (tid < 16) kf[tid] = __ldg(k4 + (3 - (tid >> 2)) * 4 + (3 - (tid & 3)));  // flipped
   if (tid == 0) {
     prefetch_tmap(&tm_u);
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
     fence_mbar_init();
   }
+  pdl_launch_dependents();   // programmatic dependent launch (sm100_ptx.cuh): global memory only after the wait
+  pdl_wait();
+  if (tid < 16) kf[tid] = __ldg(k4 + (3 - (tid >> 2)) * 4 + (3 - (tid & 3)));  // flipped
   __syncthreads();
 
   // (multiply-shift divisions: the three runtime divisions were ~75 of the ~480 instructions per thread and tile)
@@ -393,8 +395,8 @@ extern "C" int maua_blur_act_nhwc(const float* u, const float* k4, const MauaCon
 #define MAUA_BLUR_LAUNCH(RPTV, FMTV)                                                                                  \
   do {                                                                                                                \
     MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(blur_act_nhwc_tma_kernel<RPTV, FMTV>), smem));      \
-    blur_act_nhwc_tma_kernel<RPTV, FMTV><<<grid, 128 * (16 / RPTV), smem, as_stream(stream)>>>(                       \
-        tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles, f0, f1, f2);                                               \
+    MAUA_CHECK_CUDA(launch_chain(blur_act_nhwc_tma_kernel<RPTV, FMTV>, dim3(grid), dim3(128 * (16 / RPTV)), smem,     \
+                                 as_stream(stream), 1, tm, k4, *ep_host, batch, ch, hu, wu, (int)n_tiles, f0, f1, f2)); \
   } while (0)
     if (rpt != 8) MAUA_BLUR_LAUNCH(4, 2);
     else if (fmt == 0) MAUA_BLUR_LAUNCH(8, 0);

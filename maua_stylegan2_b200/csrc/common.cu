@@ -35,6 +35,11 @@ static std::mutex g_dev_mu;
 static std::map<int, int> g_sm_count;                              // device -> SM count
 static std::map<std::pair<const void*, int>, size_t> g_dyn_smem;   // (kernel, device) -> limit already set
 
+bool pdl_enabled() {   // read per call: tests and A/B runs toggle it
+  const char* e = getenv("MAUA_PDL");
+  return !(e && e[0] == '0');
+}
+
 int device_sm_count() {
   int dev = 0;
   cudaGetDevice(&dev);

@@ -131,6 +131,37 @@ __device__ __forceinline__ void st_global_v8_b32(void* p, uint32_t a0, uint32_t 
                : "memory");
 }
 
+// Programmatic dependent launch for the kernels of the synthesis chain (conv -> blur_act -> conv ...): the next kernel's
+// launch, CTA scheduling and global-memory-free setup overlap the tail of the running one (sm100_ptx.cuh: pdl_wait).
+// MAUA_PDL=0 launches them with plain stream order.  `cluster_x` > 1 adds the cluster dimension (CTA pairs).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                                Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Exact x / d for 0 <= x < 2^31 and a runtime-constant d >= 1 without the ~25-instruction integer-division sequence:
 // q = (umulhi(x, m) + x) >> s with m = floor(2^32 * (2^s - d) / d) + 1, s = ceil(log2 d)  (round-up method, 33-bit magic).
 struct FastDiv { uint32_t m, s; };

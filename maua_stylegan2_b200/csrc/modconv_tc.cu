@@ -124,6 +124,8 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();   // programmatic dependent launch: nothing above touched global memory (sm100_ptx.cuh)
+  pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -505,7 +507,8 @@ extern "C" int maua_modconv_tc(const void* x_hi, const void* x_lo, const void* w
 #define MAUA_TC_LAUNCH(KCV, UPV)                                                                                   \
   do {                                                                                                             \
     MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(modconv_tc_kernel<KCV, UPV>), smem));             \
-    modconv_tc_kernel<KCV, UPV><<<grid, 192, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep);                       \
+    MAUA_CHECK_CUDA(launch_chain(modconv_tc_kernel<KCV, UPV>, dim3(grid), dim3(192), smem, st, 1, ta_hi, ta_lo, tb_hi,  \
+                                 tb_lo, p, ep));                                                                   \
   } while (0)
   if (kc == 64) {
     if (up) MAUA_TC_LAUNCH(64, true); else MAUA_TC_LAUNCH(64, false);

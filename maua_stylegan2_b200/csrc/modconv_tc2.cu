@@ -157,6 +157,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   __syncthreads();
   if (PAIR) cluster_sync_all();   // the peer's barriers exist before any remote arrive / TMA completion targets them
   tc_fence_after();
+  // programmatic dependent launch: everything above touched no global memory
+  pdl_launch_dependents();
+  pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -860,24 +863,15 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
 #define MAUA_TC2_LAUNCH(KCV, UPV, MODEV)                                                                            \
   do {                                                                                                              \
     MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(modconv_tc2_kernel<KCV, UPV, MODEV, false>), smem)); \
-    modconv_tc2_kernel<KCV, UPV, MODEV, false><<<(unsigned)grid, THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p, ep); \
+    MAUA_CHECK_CUDA(launch_chain(modconv_tc2_kernel<KCV, UPV, MODEV, false>, dim3((unsigned)grid), dim3(THREADS), smem, st, 1, \
+                                 ta_hi, ta_lo, tb_hi, tb_lo, p, ep));                                                  \
   } while (0)
   const int mode = n_products == 1 ? 0 : (n_products == 2 ? (p.cat ? 4 : 3) : (p.cat ? 2 : 1));
 #define MAUA_TC2_LAUNCH_PAIR(KCV, UPV, MODEV)                                                                       \
   do {                                                                                                              \
     auto kern = modconv_tc2_kernel<KCV, UPV, MODEV, true>;                                                          \
     MAUA_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem));                                    \
-    cudaLaunchConfig_t cfg = {};                                                                                    \
-    cfg.gridDim = dim3((unsigned)grid);                                                                             \
-    cfg.blockDim = dim3(THREADS);                                                                                   \
-    cfg.dynamicSmemBytes = smem;                                                                                    \
-    cfg.stream = st;                                                                                                \
-    cudaLaunchAttribute attr[1];                                                                                    \
-    attr[0].id = cudaLaunchAttributeClusterDimension;                                                               \
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;                       \
-    cfg.attrs = attr;                                                                                               \
-    cfg.numAttrs = 1;                                                                                               \
-    MAUA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, p, ep));                             \
+    MAUA_CHECK_CUDA(launch_chain(kern, dim3((unsigned)grid), dim3(THREADS), smem, st, 2, ta_hi, ta_lo, tb_hi, tb_lo, p, ep)); \
   } while (0)
 #define MAUA_TC2_MODES(UPV)                                                   \
   switch (mode) {                                                             \

@@ -24,6 +24,16 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
+// is still running — as soon as every CTA of the predecessor has executed launch_dependents (or exited).  wait blocks
+// until the predecessor grid has COMPLETED and its memory is visible; without the launch attribute both are no-ops.
+// Rule used here: setup that touches no global data (barrier init, TMEM allocation, tensor-map prefetch) runs first, then
+// launch_dependents (after the TMEM allocation: a dependent CTA that got its columns first and then sat in wait would
+// starve this CTA's allocation), then wait, then everything that reads or writes global memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
