@@ -72,6 +72,7 @@ struct Params {
   // tile 2*pp + r of pixel-pair pp (n_ptiles odd: the last pair's rank 1 works on an all-out-of-range tile)
   int pair;
   int n_ptiles;          // pixel tiles = tiles_x * tiles_y * B
+  int coll;              // transposed conv, fp16 format, one phase group: taps collapsed by input shift (see c_shifts)
   int dbg;               // MAUA_TC_DBG (timing experiments, results invalid): 1 = empty epilogue, 2 = no A loads after the
                          // first, 4 = epilogue stops after the TMEM loads, 8 = epilogue without TMEM loads
 };
@@ -94,6 +95,20 @@ __constant__ TapList c_taps[8] = {
     {2, {{1, 1, 1, 0}, {0, 1, 7, 0}}},                                                          // phase 1
     {2, {{1, 1, 3, 0}, {1, 0, 5, 0}}},                                                          // phase 2
     {1, {{1, 1, 4, 0}}}};                                                                       // phase 3
+
+// "Collapsed" transposed conv (fp16 format, all four phases in one item, BN <= 64).  The nine taps read only FOUR distinct
+// input shifts (hy, hx): (1,1) feeds all four sub-pixel phases, (1,0) phases {2,0}, (0,1) phases {0,1}, (0,0) phase 0.
+// With the phase accumulators of a tile laid out side by side in TMEM in the order [ph2 | ph0 | ph1 | ph3], the taps of
+// one shift are ONE MMA of N = n*BN whose B operand is their weight tiles stacked in shared memory (n TMA boxes into one
+// stage): 4 MMAs of N = 4BN / 2BN / 2BN / BN per K-step and weight plane instead of 9 of N = BN.  Small-N MMAs are bound by
+// the 4 KB A-operand fetch (cycles ~ 32 + N/4), so 64->32 @512: 9*40 = 360 -> 64+48+48+40 = 200 cycles per K-step and plane.
+struct Shift { int8_t hy, hx, slot0, n; int8_t tap[4]; };
+__constant__ Shift c_shifts[4] = {{1, 1, 0, 4, {3, 0, 1, 4}},
+                                  {1, 0, 0, 2, {5, 2, 0, 0}},
+                                  {0, 1, 1, 2, {6, 7, 0, 0}},
+                                  {0, 0, 1, 1, {8, 0, 0, 0}}};
+// accumulator slot -> sub-pixel phase (py*2 + px), one nibble per slot: slots hold [ph2, ph0, ph1, ph3]
+constexpr uint32_t COLL_SLOT_PHASE = 0x3102u;
 
 __device__ __forceinline__ float lrelu_s(float v, float slope, float scale) { return (v > 0.f ? v : v * slope) * scale; }
 
@@ -121,7 +136,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const uint32_t a_stage = (uint32_t)p.a_planes * p.a_plane;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const int bn_cta = PAIR ? p.BN >> 1 : p.BN;    // weight rows this CTA holds per tap / K chunk
-  const uint32_t b_half = (uint32_t)bn_cta * ROW, b_stage = 2 * b_half;
+  const bool coll = UP && MODE == 3 && !PAIR && p.coll != 0;
+  // one weight plane of a B stage: BN rows (half of them per CTA of a pair); collapsed mode stacks up to 4 tap tiles
+  const uint32_t b_half = (coll ? 4u * (uint32_t)p.BN : (uint32_t)bn_cta) * ROW, b_stage = 2 * b_half;
   const uint32_t a_base = smem0;
   const uint32_t b_base = a_base + (uint32_t)p.SA * a_stage;
   const uint32_t bar_base = b_base + (uint32_t)p.SB * b_stage;
@@ -238,6 +255,22 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
         }
         if (++ia == p.SA) { ia = 0; pa ^= 1; }
+        if (coll) {   // one B stage per input shift: the weight tiles of its taps stacked, hi plane then lo plane
+          const uint32_t tile_bytes = (uint32_t)p.BN * ROW;
+#pragma unroll 1
+          for (int sf = 0; sf < 4; ++sf) {
+            const Shift sh = c_shifts[sf];
+            mbar_wait(b_empty + 8 * ib, pb ^ 1);
+            mbar_expect_tx(b_full + 8 * ib, 2u * (uint32_t)sh.n * tile_bytes);
+            const uint32_t dstb = b_base + ib * b_stage;
+            for (int j = 0; j < sh.n; ++j) {
+              tma_load_3d(dstb + j * tile_bytes, &tm_b_hi, b_full + 8 * ib, c0, n0, sh.tap[j]);
+              tma_load_3d(dstb + b_half + j * tile_bytes, &tm_b_lo, b_full + 8 * ib, c0, n0, sh.tap[j]);
+            }
+            if (++ib == p.SB) { ib = 0; pb ^= 1; }
+          }
+          continue;
+        }
 #pragma unroll 1
         for (int t = 0; t < tl.n; ++t) {
           if (p.resident_b && item != item0) break;  // weights already resident in shared memory
@@ -297,6 +330,36 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         for (int kc = 0; kc < p.n_kchunks; ++kc) {
           mbar_wait(a_full + 8 * ia, pa);
           const uint64_t da_stage = da0 + (uint64_t)ia * a_stage16;
+          if (coll) {
+#pragma unroll 1
+            for (int sf = 0; sf < 4; ++sf) {
+              const Shift sh = c_shifts[sf];
+              mbar_wait(b_full + 8 * ib, pb);
+              tc_fence_after();
+              const uint64_t dbh = db0 + (uint64_t)ib * b_stage16, dbl = dbh + b_half16;
+              const uint64_t dah0 = da_stage + (uint64_t)((uint32_t)(sh.hy * p.HW_ + sh.hx) * ROW >> 4);
+              const uint32_t idn = make_idesc_f16(128u, (uint32_t)(sh.n * p.BN));
+              // accumulators of tile r: 4 slots of BN columns side by side; the first shift touches all of them
+              const uint32_t acc0 = acc_stage + (uint32_t)(sh.slot0 * p.BN);
+              const uint32_t accumulate = (kc > 0 || sf > 0) ? 1u : 0u;
+              if (leader) {
+#pragma unroll
+                for (int r = 0; r < RR; ++r) {
+                  const uint64_t dah = dah0 + (uint64_t)r * rstep16;
+                  const uint32_t acc = acc0 + (uint32_t)(r * 4 * p.BN);
+                  mma(acc, dah, dbh, idn, accumulate);
+                  mma(acc, dah + 2, dbh + 2, idn, 1u);
+                  mma(acc, dah, dbl, idn, 1u);
+                  mma(acc, dah + 2, dbl + 2, idn, 1u);
+                }
+                commit(b_empty + 8 * ib);
+              }
+              if (++ib == p.SB) { ib = 0; pb ^= 1; }
+            }
+            if (leader) commit(a_empty + 8 * ia);
+            if (++ia == p.SA) { ia = 0; pa ^= 1; }
+            continue;
+          }
 #pragma unroll 1
           for (int t = 0; t < tl.n; ++t) {
             const Tap tp = tl.t[t];
@@ -449,8 +512,9 @@ modconv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const int first_job = fuse_rgb ? first_job_rgb : egroup;
 #pragma unroll 1
       for (int job = first_job; job < njobs; job += EPI_GROUPS) {
-        const int tile = fuse_rgb ? job : (job >> bn16_log);   // accumulator index = ph * R + r
-        const int ph = tile >> r_log, r = tile & (R - 1);
+        const int tile = fuse_rgb ? job : (job >> bn16_log);   // accumulator index = ph * R + r (collapsed: r * 4 + slot)
+        const int ph = coll ? (int)((COLL_SLOT_PHASE >> (4 * (tile & 3))) & 3u) : tile >> r_log;
+        const int r = coll ? tile >> 2 : tile & (R - 1);
         const int c_first = fuse_rgb ? 0 : ((job & (nchunk - 1)) << 4);
         const int c_end = fuse_rgb ? BN : c_first + 16;
         const int gy = y0 + r * TH + ty;
@@ -686,6 +750,16 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   int best_r = 0, best_bn = 0, best_cat = 0, best_groups = 1;
   static const int force_groups = [] { const char* e = getenv("MAUA_TC_GROUPS"); return e ? atoi(e) : 0; }();
   const uint32_t a_planes = n_products == 3 ? 2u : 1u;   // n_products: 1 = bf16 hi*hi, 3 = bf16 split, 2 = fp16 (a * (w_hi + w_lo))
+  // collapsed transposed conv (see c_shifts): fp16 format, all phases in one item, no concat, N = 4*BN <= 256
+  // OFF by default: correct (tests) but measured SLOWER on both layers it applies to — 64->32 @512 up 0.433 vs 0.354 ms,
+  // 128->64 @256 up 0.330 vs 0.256 ms, same box, same (R, BN) — although it issues 16 instead of 36 MMAs per K chunk and
+  // tile; not profiled yet (suspect: the issue loop of the collapsed form, whose descriptors are not compile-time unrolled
+  // per tap, is slower than the tensor pipe).  MAUA_TC_COLL=1 enables it.
+  const char* coll_env = getenv("MAUA_TC_COLL");
+  const bool coll_on = coll_env && coll_env[0] == '1';
+  auto is_coll = [&](int bn, int cat, int groups) {
+    return coll_on && up && n_products == 2 && !cat && groups == 1 && bn <= 64;
+  };
   auto n_ctas = [&](int r, int bn, int groups) {
     return tiles_x * ceil_div(rows16, (long long)r) * batch * (cout / bn) * groups;
   };
@@ -697,8 +771,8 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     const int blk = cat ? 2 * bn : bn;  // concat mode doubles the accumulator width
     if (r * blk * (nphase / groups) > tmem_cap) return false;
     const uint32_t plane = align1k((uint32_t)((TH * r + (up ? 1 : 2)) * (up ? TW + 1 : TW + 2) * kc * 2));
-    const uint32_t b_st = 2u * bn * kc * 2u;
-    return a_planes * plane + 4 * b_st <= budget;  // A halo (hi[+lo]) + a B ring deep enough to hide TMA latency
+    const uint32_t b_st = 2u * bn * kc * 2u * (is_coll(bn, cat, groups) ? 4u : 1u);
+    return a_planes * plane + (is_coll(bn, cat, groups) ? 3 : 4) * b_st <= budget;  // A halo + a B ring that hides TMA latency
   };
   auto search = [&]() {
     double best_cost = 1e30;
@@ -744,6 +818,8 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
       pr = 2;
       if (cout == 64) pg = up ? 2 : 1;
       else { pr = up ? 2 : 4; pg = 1; }
+      // collapsed taps (c_shifts): all four phases in one item; two accumulator stages need 4*BN*R*2 <= 512 columns
+      if (up && coll_on) { pg = 1; pr = cout == 64 ? 1 : 2; }
     }
     if (force_groups && up) pg = force_groups;
     while (pr > 1 && pr > rows16) pr >>= 1;
@@ -798,11 +874,12 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   p.pair = pair ? 1 : 0;
   p.n_ptiles = (int)(ptiles < (1LL << 30) ? ptiles : 0);
   const int bn_cta = pair ? bn / 2 : bn;
-  const uint32_t a_stage = a_planes * p.a_plane, b_stage = 2u * bn_cta * kc * 2u;
+  p.coll = is_coll(bn, p.cat, p.n_groups) ? 1 : 0;
+  const uint32_t a_stage = a_planes * p.a_plane, b_stage = 2u * bn_cta * kc * 2u * (p.coll ? 4u : 1u);
   p.SA = (2 * a_stage + 4 * b_stage <= budget) ? 2 : 1;
   int sb = (int)((budget - (uint32_t)p.SA * a_stage) / b_stage);
   // small layers: keep ALL weight tiles of the layer in shared memory for the lifetime of the persistent CTA
-  p.resident_b = (p.n_tiles == 1 && p.n_groups == 1 && 9 * n_kchunks <= sb && 9 * n_kchunks <= 36) ? 1 : 0;
+  p.resident_b = (!p.coll && p.n_tiles == 1 && p.n_groups == 1 && 9 * n_kchunks <= sb && 9 * n_kchunks <= 36) ? 1 : 0;
   if (p.resident_b) sb = 9 * n_kchunks;
   else if (sb > 12) sb = 12;
   if (sb < 2) return unsupported;
@@ -836,8 +913,8 @@ int modconv_tc2_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     fprintf(stderr, "[modconv_tc2] %s B%d %d->%d @%dx%d: R=%d BN=%d cat=%d groups=%d resB=%d AS=%d SA=%d SB=%d smem=%zuKB tmem=%u items=%lld grid=%lld\n",
             up ? "up" : "same", batch, cin, cout, h, w, R, bn, p.cat, p.n_groups, p.resident_b, p.AS, p.SA, p.SB, smem / 1024, p.tmem_cols, items, grid);
 
-  set_conv_config("v2 up=%d R=%d BN=%d cat=%d groups=%d prod=%d resB=%d AS=%d SA=%d SB=%d items=%lld grid=%lld pair=%d", up, R, bn,
-                  p.cat, p.n_groups, n_products, p.resident_b, p.AS, p.SA, p.SB, items, grid, p.pair);
+  set_conv_config("v2 up=%d R=%d BN=%d cat=%d groups=%d prod=%d resB=%d AS=%d SA=%d SB=%d items=%lld grid=%lld coll=%d pair=%d", up,
+                  R, bn, p.cat, p.n_groups, n_products, p.resident_b, p.AS, p.SA, p.SB, items, grid, p.coll, p.pair);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   const auto swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const cuuint64_t adims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};

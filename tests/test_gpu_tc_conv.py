@@ -268,6 +268,10 @@ F16_CASES = [
     ((1, 128, 128, 64, 32, True), None),         # up, mode 3
     ((2, 64, 32, 64, 40, False), ["1,32,1,1", "2,32,0,1", "4,16,1,1"]),
     ((2, 64, 32, 56, 24, True), ["1,32,1,1", "2,32,1,2", "4,32,0,4", "2,32,0,1"]),
+    # collapsed taps (one phase group, no concat, BN <= 64: 4 MMAs of N = 4BN / 2BN / 2BN / BN per K-step and plane)
+    ((2, 64, 32, 56, 24, True), ["1,32,0,1", "4,32,0,1", "1,16,0,1", "2,16,0,1"]),
+    ((1, 128, 64, 64, 48, True), ["1,64,0,1", "2,32,0,1", "1,32,0,1"]),
+    ((3, 32, 64, 33, 17, True), ["1,64,0,1", "1,32,0,1"]),          # ragged tiles, one K chunk
 ]
 
 
@@ -278,6 +282,7 @@ def test_tc2_f16_activation_format(case, forces, monkeypatch):
     b, cin, cout, h, w, up = case
     x, wt, s, d, noise, nw, bias, s_next, scale = _case_tensors(b, cin, cout, h, w, up, 300 + cin + cout + h)
     ref, raw = _reference(x, wt, s, d, noise, nw, bias, up, scale)
+    monkeypatch.setenv("MAUA_TC_COLL", "1")   # the collapsed-tap form is opt-in (measured slower): cover it here
     for f in (forces or [None]):
         if f is not None:
             monkeypatch.setenv("MAUA_TC_FORCE", f)
@@ -285,6 +290,8 @@ def test_tc2_f16_activation_format(case, forces, monkeypatch):
             y, o_hi, o_lo, u = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 2, scale, out_f16=out_f16)
             cfg = L.last_conv_config()
             assert cfg.startswith("v2 ") and " prod=2 " in cfg, cfg
+            if up and f is not None and f.endswith(",0,1") and int(f.split(",")[1]) <= 64:
+                assert " coll=1 " in cfg, cfg     # eligible forced configurations take the collapsed-tap form
             if up:
                 assert rel_err(u.cpu().numpy(), raw.numpy()) < 6e-4, "raw transposed-conv phases"
             assert not torch.isnan(y).any()
@@ -300,6 +307,26 @@ def test_tc2_f16_activation_format(case, forces, monkeypatch):
     xs, wts, ss, ds, ns, nws, bs, sns, sc = _case_tensors(2, 64, 64, 16, 16, False, 1)
     with pytest.raises(L.MauaError):
         _run_tc(xs, wts, ss, ds, ns, nws, bs, sns, False, 2, sc)
+
+
+def test_tc2_collapsed_taps_agree_with_per_tap_form(monkeypatch):
+    """MAUA_TC_COLL=0 runs the same configuration tap by tap (9 MMAs of N = BN per K-step and plane): same products, a
+    different fp32 accumulation order — the raw phases must agree to fp32 rounding, far below the fp16-operand error."""
+    from maua_stylegan2_b200 import _lib as L
+
+    b, cin, cout, h, w, up = 2, 96, 32, 56, 40, True
+    x, wt, s, d, noise, nw, bias, s_next, scale = _case_tensors(b, cin, cout, h, w, up, 4242)
+    for f in ("2,32,0,1", "1,16,0,1"):
+        monkeypatch.setenv("MAUA_TC_FORCE", f)
+        monkeypatch.setenv("MAUA_TC_COLL", "0")
+        y0, _, _, u0 = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 2, scale)
+        assert " coll=0 " in L.last_conv_config()
+        monkeypatch.setenv("MAUA_TC_COLL", "1")
+        y1, _, _, u1 = _run_tc(x, wt, s, d, noise, nw, bias, s_next, up, 2, scale)
+        assert " coll=1 " in L.last_conv_config()
+        assert not torch.isnan(u1).any() and not torch.isnan(y1).any()
+        assert rel_err(u1.cpu().numpy(), u0.cpu().numpy()) < 5e-6, f
+        assert rel_err(y1.cpu().numpy(), y0.cpu().numpy()) < 5e-6, f
 
 
 def test_f16_layout_kernels():
